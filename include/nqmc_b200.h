@@ -1,0 +1,179 @@
+/* nqmc_b200.h -- C ABI of the B200-native nqmc walker loop (libnqmc_b200.so).
+ *
+ * The reference (Sakeeb91/neural-qmc-wavefunction) has no FFI / plugin registry: its extension
+ * points are Python call signatures that drive a per-walker closure through jax.vmap / grad /
+ * hessian.  This header is the coarse, batched boundary those signatures bind to instead
+ * (SURVEY section 8(b)); every entry point cites the reference lines it replaces.  All paths are
+ * relative to /root/reference.
+ *
+ * Conventions
+ *   - plain C, no C++ / torch / XLA types.  `nqmc_stream` is a cudaStream_t passed as void*.
+ *   - every buffer is CALLER-OWNED.  Unless a name ends in `_host`, pointers are DEVICE pointers on
+ *     the ctx's device.  Calls are asynchronous on `stream`, never synchronise, never allocate
+ *     (all scratch is sized by nqmc_reserve).  `_host` entry points take HOST pointers, copy in,
+ *     run, copy out and synchronise the stream before returning (the e2e / ctypes convenience path).
+ *   - walker positions are structure-of-arrays fp32: r[(3*i + d) * W + w] for electron i, axis d,
+ *     walker w ("SoA [3N][W]").  The reference's AoS (W,N,3) row-major layout
+ *     (src/nqmc/sampler/metropolis.py:33) is converted at the edge with nqmc_aos_to_soa / _soa_to_aos.
+ *   - theta is ONE flat fp32 vector: the reference's parameter pytree flattened leaf by leaf in
+ *     sorted-key order, row-major leaves == jax.flatten_util.ravel_pytree(params)
+ *     (jax.tree.leaves order, used by the reference at src/nqmc/optimizer/vmc.py:265).
+ *     nqmc_param_count / nqmc_leaf_info describe it.  Gradients come back in the same order.
+ *   - return value: 0 ok, <0 error (codes below); message via nqmc_last_error.  No exceptions
+ *     cross the ABI.  A ctx is bound to one device, is not thread-safe; distinct ctxs are independent.
+ *   - there is NO CPU fallback: nqmc_create fails with NQMC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NQMC_B200_H
+#define NQMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQMC_ABI_VERSION 1
+
+typedef struct nqmc_ctx nqmc_ctx;
+typedef void* nqmc_stream; /* cudaStream_t */
+
+enum { NQMC_OK = 0, NQMC_ERR_ARG = -1, NQMC_ERR_CUDA = -2, NQMC_ERR_UNSUPPORTED = -3, NQMC_ERR_STATE = -4 };
+
+/* wavefunction kinds */
+enum {
+  NQMC_KIND_SIMPLE = 0,        /* SimpleWavefunction: src/nqmc/wavefunction/simple.py:73-164 */
+  NQMC_KIND_ANTISYMMETRIC = 1  /* [SPEC] AntisymmetricWavefunction: .github/phase3-issue-body.md:180-219 */
+};
+
+/* Geometry constants the path reads from the reference's Molecule
+ * (src/nqmc/systems/molecule.py:49-97: positions, charges, spin; :142-153 V_nn). */
+typedef struct {
+  int32_t n_atoms;  /* 1..16 */
+  int32_t n_elec;   /* 1..16 */
+  int32_t n_up;     /* first n_up electrons are spin-up (molecule.py:177-180) */
+  int32_t _pad;
+  const double* R;  /* host [n_atoms][3], bohr */
+  const double* Z;  /* host [n_atoms] */
+  double v_nn;      /* Molecule.nuclear_repulsion_energy() */
+} nqmc_system;
+
+/* Network shape (constructor kwargs of the reference's wavefunction classes). */
+typedef struct {
+  int32_t kind;          /* NQMC_KIND_* */
+  int32_t hidden0;       /* hidden_dims[0]; kind 1: 32, 64 or 128 */
+  int32_t hidden1;       /* hidden_dims[1]; kind 1: must equal hidden0 */
+  int32_t use_cusp;      /* kind 1: ElectronNuclearCusp + ElectronElectronCusp (phase3-issue-body.md:50-122) */
+  int32_t use_backflow;  /* kind 1: BackflowTransform (phase3-issue-body.md:134-169) */
+  int32_t _pad;
+  double envelope_decay; /* kind 0: SimpleWavefunction.envelope_decay (simple.py:102) */
+  double cusp_same;      /* e-e cusp coefficient, same spin  (spec: 0.5, phase3-issue-body.md:109) */
+  double cusp_diff;      /* e-e cusp coefficient, opposite   (spec: 0.25, :110) */
+} nqmc_net;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+
+/* Replaces: wavefunction / Molecule construction (scripts/train_h2.py:155-169). */
+int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ctx** out);
+int nqmc_destroy(nqmc_ctx* ctx);
+const char* nqmc_last_error(const nqmc_ctx* ctx); /* ctx may be NULL: last create() error */
+int nqmc_abi_version(void);
+
+/* Size all internal scratch for batches of up to max_walkers walkers (the only allocating call). */
+int nqmc_reserve(nqmc_ctx* ctx, int64_t max_walkers);
+
+/* ---- parameters ------------------------------------------------------------------------------ */
+
+/* Number of scalars P in theta (== sum of leaf sizes of wf.init(...), simple.py:166-176). */
+int64_t nqmc_param_count(const nqmc_ctx* ctx);
+/* Leaf `index` (0-based, sorted-key order): writes its '/'-joined path (NUL-terminated, truncated to
+ * cap), rank-2 shape (rows, cols; scalar leaves are 1 x 1) and offset into theta.
+ * Returns the number of leaves when index < 0. */
+int64_t nqmc_leaf_info(const nqmc_ctx* ctx, int index, char* path, size_t cap, int64_t* rows, int64_t* cols,
+                       int64_t* offset);
+/* Upload theta (P floats).  `theta` is a device pointer; `theta_host` variant takes host memory. */
+int nqmc_set_params(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream stream);
+int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta_host, int64_t P, nqmc_stream stream);
+
+/* ---- layout helpers -------------------------------------------------------------------------- */
+int nqmc_aos_to_soa(nqmc_ctx* ctx, const float* aos, float* soa, int64_t W, nqmc_stream stream);
+int nqmc_soa_to_aos(nqmc_ctx* ctx, const float* soa, float* aos, int64_t W, nqmc_stream stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* log|psi| and sign for W walkers.
+ * Replaces: vmap(wavefunction(params, r)) -- src/nqmc/wavefunction/base.py:38-48, simple.py:151-164,
+ * [SPEC] phase3-issue-body.md:196-219.  `sign` may be NULL. */
+int nqmc_log_psi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, float* sign, nqmc_stream stream);
+
+/* One all-electron Metropolis-Hastings move for every walker, in place.
+ * Replaces: MetropolisSampler.step -- src/nqmc/sampler/metropolis.py:115-147
+ *   proposals = r + sigma * normal ; accept = log(u) < 2 log|psi'| - logp  (strict, fp32).
+ * normals : SoA [3N][W] N(0,1) draws, or NULL -> on-device Philox4x32-10 keyed by (seed, step,
+ *           walker_id0 + w) (parity mode supplies the reference's streams)
+ * uniforms: [W] U[0,1) draws, or NULL (same Philox stream)
+ * logp    : [W] current log|psi|^2, updated where accepted (carries the reference's stale-logp
+ *           behaviour across parameter updates, SURVEY A.5, because it is caller state)
+ * accept  : [W] 0/1 per walker, may be NULL ; n_accepted: [W] fp32 += accept, may be NULL (:140) */
+int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
+                 uint64_t step, int64_t walker_id0, float sigma, int64_t W, uint8_t* accept, float* n_accepted,
+                 nqmc_stream stream);
+
+/* Local energy E_L = T + V_en + V_ee + V_nn with the analytic forward-mode Laplacian.
+ * Replaces: local_energy_batched / kinetic_energy / electron_nuclear_potential /
+ * electron_electron_potential -- src/nqmc/hamiltonian/molecular.py:52-69,87-102,116-135,159-197.
+ * parts (may be NULL): SoA [4][W] = T, V_en, V_ee, log|psi|. */
+int nqmc_local_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, nqmc_stream stream);
+
+/* out[p] = sum_w weight[w] * d log|psi(r_w)| / d theta_p      (fp64 result, P entries)
+ * Replaces: vmap(jax.grad(lambda p: wavefunction(p, r)))(samples) followed by the weighted mean --
+ * src/nqmc/optimizer/vmc.py:120-133 -- without materialising the (n_total x P) matrix.
+ * weight NULL -> all ones (gives sum_w O_w). */
+int nqmc_grad_accum(nqmc_ctx* ctx, const float* r, const float* weight, int64_t W, double* out, nqmc_stream stream);
+
+/* Reduction header written by nqmc_energy_stats / nqmc_walker_step (8 doubles, all additive across ranks). */
+enum {
+  NQMC_HDR_N = 0,        /* walkers with finite E_L */
+  NQMC_HDR_SUM_E = 1,    /* sum E_L over those */
+  NQMC_HDR_SUM_E2 = 2,   /* sum E_L^2 */
+  NQMC_HDR_N_ACCEPT = 3, /* accepted moves in this step */
+  NQMC_HDR_N_BAD = 4,    /* walkers whose E_L was not finite (excluded from the sums) */
+  NQMC_HDR_SIZE = 8
+};
+
+/* hdr[0..7] from e_l[W] (N_ACCEPT left 0).  Replaces jnp.mean / jnp.std in vmc.py:113-114. */
+int nqmc_energy_stats(nqmc_ctx* ctx, const float* e_l, int64_t W, double* hdr, nqmc_stream stream);
+
+/* The fused walker step = one sample of VMCOptimizer.step's inner work (vmc.py:242-253):
+ *   phase A (nqmc_walker_step_a): MH move (as nqmc_mh_step) -> E_L at the new position -> hdr.
+ *   [multi-GPU: the caller all-reduces hdr (8 doubles) here -- the only exchange before phase B]
+ *   phase B (nqmc_walker_step_b): gsum[p] = sum_w (E_w - hdr.SUM_E/hdr.N) * O_w[p]   (fp64, P entries)
+ *   [multi-GPU: the caller all-reduces gsum];  gradient = 2 * gsum / hdr.N  (vmc.py:126-133).
+ * nqmc_walker_step runs A then B back to back (single GPU). */
+int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms,
+                       uint64_t seed, uint64_t step, int64_t walker_id0, float sigma, int64_t W, float* e_l,
+                       float* n_accepted, double* hdr, nqmc_stream stream);
+int nqmc_walker_step_b(nqmc_ctx* ctx, const float* r, const float* e_l, int64_t W, const double* hdr, double* gsum,
+                       nqmc_stream stream);
+int nqmc_walker_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
+                     uint64_t step, int64_t walker_id0, float sigma, int64_t W, float* e_l, float* n_accepted,
+                     double* hdr, double* gsum, nqmc_stream stream);
+
+/* Host-buffer variant of nqmc_walker_step: r_aos_host is the reference's (W,N,3) AoS array; copies
+ * H2D, converts, steps, converts back, copies r / logp / e_l / hdr / gsum D2H, synchronises.
+ * normals_aos_host (W,N,3) / uniforms_host (W) may be NULL (device Philox). */
+int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, const float* normals_aos_host,
+                          const float* uniforms_host, uint64_t seed, uint64_t step, int64_t walker_id0, float sigma,
+                          int64_t W, float* e_l_host, double* hdr_host, double* gsum_host, nqmc_stream stream);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+/* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
+int64_t nqmc_launch_count(const nqmc_ctx* ctx);
+/* Fill normals SoA [3N][W] / uniforms [W] from the device Philox stream (for RNG parity tests). */
+int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t walker_id0, int64_t W, float* normals,
+                  float* uniforms, nqmc_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQMC_B200_H */

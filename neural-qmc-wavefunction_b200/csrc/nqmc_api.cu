@@ -1,0 +1,466 @@
+// nqmc_api.cu -- the C ABI of include/nqmc_b200.h: context, parameter map, entry points.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "nqmc_internal.cuh"
+
+
+static std::string g_create_err;
+
+namespace {
+
+struct LeafBuilder {
+  std::vector<LeafInfo>& leaves;
+  int64_t off = 0;
+  int add(const std::string& path, int64_t rows, int64_t cols) {
+    leaves.push_back({path, rows, cols, off});
+    int o = (int)off;
+    off += rows * cols;
+    return o;
+  }
+  // flax Dense: 'bias' (out,) sorts before 'kernel' (in,out)
+  void dense(const std::string& prefix, int in, int out, int& b, int& k) {
+    b = add(prefix + "/bias", 1, out);
+    k = add(prefix + "/kernel", in, out);
+  }
+  MlpOff mlp3(const std::string& prefix, int F, int H) {
+    MlpOff o;
+    dense(prefix + "/Dense_0", F, H, o.b1, o.W1);
+    dense(prefix + "/Dense_1", H, H, o.b2, o.W2);
+    dense(prefix + "/Dense_2", H, 1, o.b3, o.W3);
+    return o;
+  }
+};
+
+// Builds the sorted-key (jax.tree.leaves) parameter map.  Mirrors oracle/layout.py::leaf_table,
+// which tests/test_abi_layout.py checks it against.
+void build_param_map(nqmc_ctx* ctx) {
+  DevSys& s = ctx->sys;
+  LeafBuilder lb{ctx->leaves};
+  if (s.kind == NQMC_KIND_SIMPLE) {
+    s.simple = lb.mlp3("params", 3 * s.N, s.H);
+    s.P = (int)lb.off;
+    return;
+  }
+  if (s.use_bf) s.bf = lb.mlp3("params/backflow", 2, NQMC_BF_H);
+  if (s.use_cusp) {
+    s.ee_cusp_b = lb.add("params/ee_cusp/b_ee", 1, 1);
+    std::vector<std::pair<std::string, int>> names;
+    for (int d = 0; d < 2 * s.A; ++d) names.push_back({"Dense_" + std::to_string(d), d});
+    std::sort(names.begin(), names.end());
+    for (auto& nd : names) {
+      const int d = nd.second, a = d / 2;
+      if (d % 2 == 0) lb.dense("params/en_cusp/" + nd.first, 3, NQMC_CUSP_H, s.en_cusp_b0[a], s.en_cusp_W0[a]);
+      else lb.dense("params/en_cusp/" + nd.first, NQMC_CUSP_H, 1, s.en_cusp_b1[a], s.en_cusp_W1[a]);
+    }
+  }
+  s.jas_a_ee = lb.add("params/jastrow/a_ee", 1, 1);
+  s.jas_a_en = lb.add("params/jastrow/a_en", 1, 1);
+  s.jas_b_ee = lb.add("params/jastrow/b_ee", 1, 1);
+  s.jas_b_en = lb.add("params/jastrow/b_en", 1, 1);
+  for (int k = 0; k < s.n_dn; ++k)
+    s.mlp[s.n_up + k] = lb.mlp3("params/orbitals_down/orbital_" + std::to_string(k), s.F, s.H);
+  for (int k = 0; k < s.n_up; ++k) s.mlp[k] = lb.mlp3("params/orbitals_up/orbital_" + std::to_string(k), s.F, s.H);
+  s.P = (int)lb.off;
+}
+
+inline cudaStream_t S(nqmc_stream st) { return reinterpret_cast<cudaStream_t>(st); }
+
+int check_w(nqmc_ctx* ctx, int64_t W) {
+  if (!ctx) return NQMC_ERR_ARG;
+  if (W <= 0) {
+    ctx->err = "W must be positive";
+    return NQMC_ERR_ARG;
+  }
+  if (W > ctx->cap_w) {
+    ctx->err = "W exceeds the reserved capacity; call nqmc_reserve first";
+    return NQMC_ERR_STATE;
+  }
+  return NQMC_OK;
+}
+
+void free_scratch(nqmc_ctx* c) {
+  void* ptrs[] = {c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
+                  c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
+                  c->part_mlp, c->hdr_tmp};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
+  c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
+  c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = nullptr;
+  c->part_mlp = nullptr;
+  c->cap_w = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nqmc_abi_version(void) { return NQMC_ABI_VERSION; }
+
+const char* nqmc_last_error(const nqmc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ctx** out) {
+  if (!sys || !net || !out) {
+    g_create_err = "null argument";
+    return NQMC_ERR_ARG;
+  }
+  *out = nullptr;
+  if (sys->n_atoms < 1 || sys->n_atoms > NQMC_MAX_ATOMS || sys->n_elec < 1 || sys->n_elec > NQMC_MAX_ELEC ||
+      sys->n_up < 0 || sys->n_up > sys->n_elec || !sys->R || !sys->Z) {
+    g_create_err = "system out of range (1..16 atoms, 1..16 electrons, 0 <= n_up <= n_elec)";
+    return NQMC_ERR_ARG;
+  }
+  const int n_dn = sys->n_elec - sys->n_up;
+  if (sys->n_up > NQMC_MAX_NS || n_dn > NQMC_MAX_NS) {
+    g_create_err = "more than 8 electrons per spin are not supported";
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  if (net->kind != NQMC_KIND_SIMPLE && net->kind != NQMC_KIND_ANTISYMMETRIC) {
+    g_create_err = "unknown wavefunction kind";
+    return NQMC_ERR_ARG;
+  }
+  if (net->hidden0 != net->hidden1) {
+    g_create_err = "hidden_dims must be two equal widths";
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  if (net->kind == NQMC_KIND_ANTISYMMETRIC) {
+    if (net->hidden0 != 32 && net->hidden0 != 64 && net->hidden0 != 128) {
+      g_create_err = "orbital hidden width must be 32, 64 or 128";
+      return NQMC_ERR_UNSUPPORTED;
+    }
+    if (3 + 2 * sys->n_atoms > net->hidden0) {
+      g_create_err = "3 + 2*n_atoms orbital features must not exceed the hidden width";
+      return NQMC_ERR_UNSUPPORTED;
+    }
+    if (net->use_backflow) {
+      g_create_err = "backflow is not implemented yet in this build";
+      return NQMC_ERR_UNSUPPORTED;
+    }
+  } else if (net->hidden0 < 1 || net->hidden0 > 128) {
+    g_create_err = "SimpleWavefunction hidden width must be in 1..128";
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return NQMC_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "device index out of range";
+    return NQMC_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return NQMC_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_err = "device is not sm_100 (this library is built for B200 only)";
+    return NQMC_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return NQMC_ERR_CUDA;
+  }
+  nqmc_ctx* ctx = new nqmc_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  DevSys& s = ctx->sys;
+  memset(&s, 0, sizeof(s));
+  s.A = sys->n_atoms;
+  s.N = sys->n_elec;
+  s.n_up = sys->n_up;
+  s.n_dn = n_dn;
+  s.kind = net->kind;
+  s.H = net->hidden0;
+  s.use_cusp = net->kind == NQMC_KIND_ANTISYMMETRIC ? (net->use_cusp != 0) : 0;
+  s.use_bf = 0;
+  s.F = net->kind == NQMC_KIND_ANTISYMMETRIC ? 3 + 2 * s.A : 3 * s.N;
+  s.n_mlp = s.n_up + s.n_dn;
+  s.n_ent = s.n_up * s.n_up + s.n_dn * s.n_dn;
+  s.v_nn = (float)sys->v_nn;
+  s.env_alpha = (float)net->envelope_decay;
+  s.cusp_same = (float)net->cusp_same;
+  s.cusp_diff = (float)net->cusp_diff;
+  for (int a = 0; a < s.A; ++a) {
+    for (int d = 0; d < 3; ++d) s.R[3 * a + d] = (float)sys->R[3 * a + d];
+    s.Z[a] = (float)sys->Z[a];
+  }
+  build_param_map(ctx);
+  ctx->p_mlp = s.kind == NQMC_KIND_ANTISYMMETRIC ? (s.F * s.H + s.H + s.H * s.H + s.H + s.H + 1) : s.P;
+  e = cudaMalloc(&ctx->theta, sizeof(float) * (size_t)s.P);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaMalloc(theta): ") + cudaGetErrorString(e);
+    delete ctx;
+    return NQMC_ERR_CUDA;
+  }
+  cudaMemset(ctx->theta, 0, sizeof(float) * (size_t)s.P);
+  *out = ctx;
+  return NQMC_OK;
+}
+
+int nqmc_destroy(nqmc_ctx* ctx) {
+  if (!ctx) return NQMC_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  free_scratch(ctx);
+  if (ctx->theta) cudaFree(ctx->theta);
+  delete ctx;
+  return NQMC_OK;
+}
+
+int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
+  if (!ctx || W <= 0) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if (W <= ctx->cap_w) return NQMC_OK;
+  free_scratch(ctx);
+  const DevSys& s = ctx->sys;
+  const size_t nn = 3 * (size_t)s.N, w = (size_t)W, f = sizeof(float);
+  const size_t n_ent = s.n_ent > 0 ? s.n_ent : 1;
+  NQMC_CUDA(cudaMalloc(&ctx->r_prop, nn * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->phi, 5 * n_ent * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->inv, n_ent * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->logabs, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->sign, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->e_scratch, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->wgt, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->r_soa, nn * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->nrm_soa, nn * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->aos_stage, nn * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->uni_stage, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->logp_stage, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->nacc_stage, w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double)));
+  NQMC_CUDA(cudaMalloc(&ctx->hdr_tmp, NQMC_HDR_SIZE * sizeof(double)));
+  NQMC_CUDA(cudaMalloc(&ctx->gsum_stage, (size_t)s.P * sizeof(double)));
+  ctx->n_blk_walk = 65536;
+  NQMC_CUDA(cudaMalloc(&ctx->part_walk, (size_t)ctx->n_blk_walk * 16 * sizeof(double)));
+  ctx->n_cta_bwd = 2 * ctx->sm_count;
+  NQMC_CUDA(cudaMalloc(&ctx->part_mlp, (size_t)ctx->n_cta_bwd * ctx->p_mlp * f));
+  ctx->cap_w = W;
+  return NQMC_OK;
+}
+
+int64_t nqmc_param_count(const nqmc_ctx* ctx) { return ctx ? ctx->sys.P : -1; }
+
+int64_t nqmc_leaf_info(const nqmc_ctx* ctx, int index, char* path, size_t cap, int64_t* rows, int64_t* cols,
+                       int64_t* offset) {
+  if (!ctx) return NQMC_ERR_ARG;
+  if (index < 0) return (int64_t)ctx->leaves.size();
+  if (index >= (int)ctx->leaves.size()) return NQMC_ERR_ARG;
+  const LeafInfo& l = ctx->leaves[index];
+  if (path && cap > 0) {
+    strncpy(path, l.path.c_str(), cap - 1);
+    path[cap - 1] = 0;
+  }
+  if (rows) *rows = l.rows;
+  if (cols) *cols = l.cols;
+  if (offset) *offset = l.offset;
+  return NQMC_OK;
+}
+
+int nqmc_set_params(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream st) {
+  if (!ctx || !theta) return NQMC_ERR_ARG;
+  if (P != ctx->sys.P) {
+    ctx->err = "theta has the wrong length";
+    return NQMC_ERR_ARG;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyDeviceToDevice, S(st)));
+  return NQMC_OK;
+}
+
+int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream st) {
+  if (!ctx || !theta) return NQMC_ERR_ARG;
+  if (P != ctx->sys.P) {
+    ctx->err = "theta has the wrong length";
+    return NQMC_ERR_ARG;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyHostToDevice, S(st)));
+  NQMC_CUDA(cudaStreamSynchronize(S(st)));
+  return NQMC_OK;
+}
+
+int nqmc_aos_to_soa(nqmc_ctx* ctx, const float* aos, float* soa, int64_t W, nqmc_stream st) {
+  if (!ctx || !aos || !soa || W <= 0) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_aos_soa(ctx, aos, soa, W, true, S(st));
+}
+int nqmc_soa_to_aos(nqmc_ctx* ctx, const float* soa, float* aos, int64_t W, nqmc_stream st) {
+  if (!ctx || !aos || !soa || W <= 0) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_aos_soa(ctx, soa, aos, W, false, S(st));
+}
+
+int nqmc_log_psi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, float* sign, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !logabs) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->sys.kind == NQMC_KIND_SIMPLE) {
+    rc = nq_simple_logpsi(ctx, r, W, logabs, S(st));
+    if (rc) return rc;
+    if (sign) rc = nq_fill(ctx, sign, 1.0f, W, S(st));   // psi = exp(real) > 0
+    return rc;
+  }
+  rc = nq_launch_orb_eval(ctx, r, W, 1, ctx->phi, S(st));
+  if (rc) return rc;
+  return nq_launch_assemble(ctx, r, W, nullptr, nullptr, false, logabs, sign, S(st));
+}
+
+static int mh_core(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
+                   uint64_t step, int64_t wid0, float sigma, int64_t W, uint8_t* accept, float* n_acc,
+                   cudaStream_t st) {
+  int rc = nq_launch_propose(ctx, r, normals, seed, step, wid0, sigma, W, ctx->r_prop, st);
+  if (rc) return rc;
+  if (ctx->sys.kind == NQMC_KIND_SIMPLE) {
+    rc = nq_simple_logpsi(ctx, ctx->r_prop, W, ctx->logabs, st);
+    if (rc) return rc;
+    return nq_accept_logabs(ctx, r, logp, ctx->r_prop, ctx->logabs, uniforms, seed, step, wid0, W, accept, n_acc, st);
+  }
+  rc = nq_launch_orb_eval(ctx, ctx->r_prop, W, 1, ctx->phi, st);
+  if (rc) return rc;
+  return nq_launch_accept(ctx, r, logp, ctx->r_prop, uniforms, seed, step, wid0, W, accept, n_acc, st);
+}
+
+int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
+                 uint64_t step, int64_t wid0, float sigma, int64_t W, uint8_t* accept, float* n_acc, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !logp) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, accept, n_acc, S(st));
+}
+
+static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
+  if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
+  int rc = nq_launch_orb_eval(ctx, r, W, 5, ctx->phi, st);
+  if (rc) return rc;
+  return nq_launch_assemble(ctx, r, W, e_l, parts, true, nullptr, nullptr, st);
+}
+
+int nqmc_local_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !e_l) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return energy_core(ctx, r, W, e_l, parts, S(st));
+}
+
+// reverse pass given that ctx->inv already holds the inverse orbital matrices for r
+static int grads_core(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
+                      double* out, cudaStream_t st) {
+  NQMC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)ctx->sys.P, st));
+  if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  int rc = nq_launch_orb_bwd(ctx, r, wgt, hdr, e_l, W, out, st);
+  if (rc) return rc;
+  return nq_launch_walker_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+}
+
+int nqmc_grad_accum(nqmc_ctx* ctx, const float* r, const float* weight, int64_t W, double* out, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !out) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC) {
+    rc = nq_launch_orb_eval(ctx, r, W, 1, ctx->phi, S(st));
+    if (rc) return rc;
+    rc = nq_launch_assemble_inv(ctx, r, W, S(st));
+    if (rc) return rc;
+  }
+  return grads_core(ctx, r, weight, nullptr, nullptr, W, out, S(st));
+}
+
+int nqmc_energy_stats(nqmc_ctx* ctx, const float* e_l, int64_t W, double* hdr, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!e_l || !hdr) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_launch_stats(ctx, e_l, nullptr, W, hdr, S(st));
+}
+
+int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms,
+                       uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, float* n_acc,
+                       double* hdr, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !logp || !e_l || !hdr) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  rc = mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, nullptr, n_acc, S(st));
+  if (rc) return rc;
+  rc = energy_core(ctx, r, W, e_l, nullptr, S(st));
+  if (rc) return rc;
+  return nq_launch_stats(ctx, e_l, ctx->wgt, W, hdr, S(st));
+}
+
+int nqmc_walker_step_b(nqmc_ctx* ctx, const float* r, const float* e_l, int64_t W, const double* hdr, double* gsum,
+                       nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !e_l || !hdr || !gsum) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return grads_core(ctx, r, nullptr, hdr, e_l, W, gsum, S(st));
+}
+
+int nqmc_walker_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
+                     uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, float* n_acc, double* hdr,
+                     double* gsum, nqmc_stream st) {
+  int rc = nqmc_walker_step_a(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, e_l, n_acc, hdr, st);
+  if (rc) return rc;
+  return nqmc_walker_step_b(ctx, r, e_l, W, hdr, gsum, st);
+}
+
+int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float* normals_aos, const float* uniforms,
+                          uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, double* hdr,
+                          double* gsum, nqmc_stream st_) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r_aos || !logp || !e_l || !hdr || !gsum) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = S(st_);
+  const size_t nn = 3 * (size_t)ctx->sys.N, w = (size_t)W, f = sizeof(float);
+  NQMC_CUDA(cudaMemcpyAsync(ctx->aos_stage, r_aos, nn * w * f, cudaMemcpyHostToDevice, st));
+  rc = nq_aos_soa(ctx, ctx->aos_stage, ctx->r_soa, W, true, st);
+  if (rc) return rc;
+  const float* nrm = nullptr;
+  if (normals_aos) {
+    NQMC_CUDA(cudaMemcpyAsync(ctx->aos_stage, normals_aos, nn * w * f, cudaMemcpyHostToDevice, st));
+    rc = nq_aos_soa(ctx, ctx->aos_stage, ctx->nrm_soa, W, true, st);
+    if (rc) return rc;
+    nrm = ctx->nrm_soa;
+  }
+  const float* uni = nullptr;
+  if (uniforms) {
+    NQMC_CUDA(cudaMemcpyAsync(ctx->uni_stage, uniforms, w * f, cudaMemcpyHostToDevice, st));
+    uni = ctx->uni_stage;
+  }
+  NQMC_CUDA(cudaMemcpyAsync(ctx->logp_stage, logp, w * f, cudaMemcpyHostToDevice, st));
+  rc = nqmc_walker_step(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
+                        ctx->hdr_stage, ctx->gsum_stage, st_);
+  if (rc) return rc;
+  rc = nq_aos_soa(ctx, ctx->r_soa, ctx->aos_stage, W, false, st);
+  if (rc) return rc;
+  NQMC_CUDA(cudaMemcpyAsync(r_aos, ctx->aos_stage, nn * w * f, cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaMemcpyAsync(logp, ctx->logp_stage, w * f, cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaMemcpyAsync(e_l, ctx->e_scratch, w * f, cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaMemcpyAsync(hdr, ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaMemcpyAsync(gsum, ctx->gsum_stage, (size_t)ctx->sys.P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaStreamSynchronize(st));
+  return NQMC_OK;
+}
+
+int64_t nqmc_launch_count(const nqmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, float* normals, float* uniforms,
+                  nqmc_stream st) {
+  if (!ctx || W <= 0) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_rng_fill(ctx, seed, step, wid0, W, normals, uniforms, S(st));
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// nqmc_internal.cuh -- shared device/host definitions for libnqmc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nqmc_b200.h"
+
+#define NQMC_MAX_ATOMS 16
+#define NQMC_MAX_ELEC 16
+#define NQMC_MAX_NS 8    // electrons per spin
+#define NQMC_MAX_MLP 16  // n_up + n_dn orbital networks
+#define NQMC_CUSP_H 16
+#define NQMC_BF_H 16
+
+// ---------------------------------------------------------------------------------------------
+// Parameter map: offsets of every block inside the flat theta vector (sorted-key pytree order;
+// inside one flax Dense, 'bias' sorts before 'kernel').
+struct MlpOff {     // one Dense(F,H)-tanh-Dense(H,H)-tanh-Dense(H,1) network
+  int b1, W1, b2, W2, b3, W3;
+};
+
+struct DevSys {     // passed by value to kernels (<= 4 KB kernel-parameter budget)
+  int A, N, n_up, n_dn;
+  int kind, H, use_cusp, use_bf;
+  int F;            // kind 1: 3 + 2A orbital input features ; kind 0: 3N
+  int n_mlp;        // n_up + n_dn
+  int n_ent;        // n_up^2 + n_dn^2 entries of the two orbital matrices
+  int P;
+  float v_nn, env_alpha, cusp_same, cusp_diff;
+  float R[NQMC_MAX_ATOMS * 3];
+  float Z[NQMC_MAX_ATOMS];
+  // theta offsets
+  int jas_a_ee, jas_a_en, jas_b_ee, jas_b_en;
+  int ee_cusp_b;
+  int en_cusp_b0[NQMC_MAX_ATOMS], en_cusp_W0[NQMC_MAX_ATOMS], en_cusp_b1[NQMC_MAX_ATOMS], en_cusp_W1[NQMC_MAX_ATOMS];
+  MlpOff bf;                   // backflow eta network (F=2, H=16)
+  MlpOff simple;               // kind 0 network
+  MlpOff mlp[NQMC_MAX_MLP];    // m < n_up: spin-up orbital m ; else spin-down orbital m - n_up
+};
+
+// entry index of (spin, electron-in-spin i, orbital k) in the orbital scratch
+__host__ __device__ inline int ent_index(const DevSys& s, int spin, int i, int k) {
+  return spin == 0 ? i * s.n_up + k : s.n_up * s.n_up + i * s.n_dn + k;
+}
+
+struct LeafInfo {
+  std::string path;
+  int64_t rows, cols, offset;
+};
+
+struct nqmc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  DevSys sys{};
+  std::vector<LeafInfo> leaves;
+  std::string err;
+  int64_t launches = 0;
+  // device state
+  float* theta = nullptr;      // [P]
+  int64_t cap_w = 0;           // reserved walkers
+  float* r_prop = nullptr;     // [3N][cap_w]
+  float* phi = nullptr;        // [5][n_ent][cap_w]  orbital value / grad xyz / laplacian
+  float* inv = nullptr;        // [n_ent][cap_w]     inverse orbital matrices (seeds of the reverse pass)
+  float* logabs = nullptr;     // [cap_w]
+  float* sign = nullptr;       // [cap_w]
+  float* e_scratch = nullptr;  // [cap_w]
+  float* wgt = nullptr;        // [cap_w]
+  float* r_soa = nullptr;      // [3N][cap_w]  (host-entry staging)
+  float* nrm_soa = nullptr;    // [3N][cap_w]
+  float* aos_stage = nullptr;  // [cap_w][N][3]
+  float* uni_stage = nullptr;  // [cap_w]
+  float* logp_stage = nullptr; // [cap_w]
+  float* nacc_stage = nullptr; // [cap_w]
+  double* hdr_stage = nullptr; // [8]
+  double* gsum_stage = nullptr;// [P]
+  double* part_walk = nullptr; // [n_blk_walk][NPART_WALK] per-block partial sums of the per-walker kernels
+  int n_blk_walk = 0;
+  float* part_mlp = nullptr;   // [n_cta_bwd][P_mlp_max] per-CTA partial weight gradients
+  int n_cta_bwd = 0;
+  int p_mlp = 0;               // scalars in one orbital network
+  double* hdr_tmp = nullptr;   // [8]
+};
+
+// ---------------------------------------------------------------------------------------------
+#define NQMC_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                                 \
+      return NQMC_ERR_CUDA;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+#define NQMC_LAUNCH_CHECK()                                                                          \
+  do {                                                                                               \
+    ctx->launches++;                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess) {                                                                         \
+      ctx->err = std::string("kernel launch: ") + cudaGetErrorString(_e);                            \
+      return NQMC_ERR_CUDA;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device math
+__device__ __forceinline__ float nq_tanh(float x) {
+  // tanh(x) = 1 - 2/(exp(2x)+1); ex2.approx + rcp.approx: abs error ~1e-7, saturates cleanly.
+  float e = exp2f(2.885390081777927f * x);      // 2*log2(e)
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& n0, float& n1) {
+  float a = ((float)(x0 >> 8) + 1.0f) * 5.9604644775390625e-8f;   // (0,1]
+  float b = (float)(x1 >> 8) * 5.9604644775390625e-8f;            // [0,1)
+  float rad = sqrtf(-2.0f * logf(a));
+  float s, c;
+  sincospif(2.0f * b, &s, &c);
+  n0 = rad * c;
+  n1 = rad * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels' host launchers (defined across the .cu files)
+int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st);
+int nq_launch_orb_bwd(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
+                      int64_t W, double* out, cudaStream_t st);
+int nq_launch_propose(nqmc_ctx* ctx, const float* r, const float* normals, uint64_t seed, uint64_t step,
+                      int64_t wid0, float sigma, int64_t W, float* r_prop, cudaStream_t st);
+int nq_launch_accept(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, const float* uniforms, uint64_t seed,
+                     uint64_t step, int64_t wid0, int64_t W, uint8_t* accept, float* n_acc, cudaStream_t st);
+int nq_launch_assemble(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, bool want_energy,
+                       float* logabs, float* sign, cudaStream_t st);
+int nq_launch_stats(nqmc_ctx* ctx, const float* e_l, const float* n_acc_flags, int64_t W, double* hdr, cudaStream_t st);
+int nq_launch_walker_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center,
+                           const float* e_l, int64_t W, double* out, cudaStream_t st);
+int nq_simple_logpsi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, cudaStream_t st);
+int nq_simple_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
+int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
+                    int64_t W, double* out, cudaStream_t st);
+int nq_aos_soa(nqmc_ctx* ctx, const float* src, float* dst, int64_t W, bool to_soa, cudaStream_t st);
+int nq_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, float* normals, float* uniforms,
+                cudaStream_t st);
+int nq_fill(nqmc_ctx* ctx, float* dst, float v, int64_t n, cudaStream_t st);
+int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, const float* logabs_prop,
+                     const float* uniforms, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, uint8_t* accept,
+                     float* n_acc, cudaStream_t st);
+int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);

@@ -1,0 +1,3 @@
+from .vmc import VMCOptimizer, VMCState, compute_gradient, estimate_energy
+
+__all__ = ["VMCOptimizer", "VMCState", "compute_gradient", "estimate_energy"]
