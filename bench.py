@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- walker-steps/s of the nqmc VMC walker loop on B200 (BASELINE.json metric).
+
+One "step" = one walker-step for every walker of the batch: one Metropolis-Hastings
+proposal + accept/reject (value-only psi), the local energy E_L at the resulting position (forward
+Laplacian), and the weighted log-derivative gradient accumulation sum_w (E_w - <E>) O_w, with the
+per-iteration all-reduces of the energy header and the gradient vector when N > 1.
+
+Workload at every N: BASELINE configs[1] -- H4 linear chain (2 up, 2 down, R = 1.8 bohr), neural
+Slater-Jastrow with (64,64) orbital networks (P = 19,976), 65,536 walkers PER GPU (weak scaling),
+synthetic walkers (nuclei + 0.5 N(0,1), then >= 100 device MH burn-in steps), LeCun-normal weights.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (CPU restatement of the reference algorithm)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "neural-qmc-wavefunction_b200"))
+
+N_ATOMS, BOND, HIDDEN, SIGMA = 4, 1.8, 64, 0.5          # step_size 0.5 for H4 (phase4-issue-body.md:139)
+WALKERS_PER_GPU = 65536
+SEED = 42                                               # scripts/train_h2.py:63
+
+
+def algorithmic_flops_per_walker_step(n_atoms, hidden, n_elec, backflow=False):
+    """SURVEY 8(d) / BASELINE.md section 3: 2 m E (3 + c)."""
+    F = 3 + 2 * n_atoms
+    m = F * hidden + hidden * hidden + hidden
+    E = 2 * (n_elec // 2) ** 2
+    c = 10 if backflow else 5
+    return 2.0 * m * E * (3 + c), 2.0 * m * E
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_problem():
+    from nqmc_b200.systems import hydrogen_chain
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction
+    from nqmc_b200 import random as nqrandom
+    from nqmc_b200.params import ravel
+    mol = hydrogen_chain(N_ATOMS, BOND)
+    wf = AntisymmetricWavefunction(n_up=2, n_down=2, orbital_hidden_dims=(HIDDEN, HIDDEN), molecule=mol)
+    params = wf.init(nqrandom.PRNGKey(SEED))
+    return mol, wf, params, ravel(params)
+
+
+def initial_walkers(mol, n, lo, seed=SEED):
+    """electron i at nucleus i % A + 0.5 N(0,1) (optimizer/vmc.py:199-208), keyed by global walker id."""
+    rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, lo]))
+    R = np.asarray(mol.positions, dtype=np.float32)
+    init = np.stack([R[i % mol.n_atoms] for i in range(mol.n_electrons)], axis=0)
+    return (init[None] + 0.5 * rng.standard_normal((n, mol.n_electrons, 3))).astype(np.float32)
+
+
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nqmc_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    Wl = args.walkers_per_gpu
+    lo = rank * Wl
+    mol, wf, params, theta = make_problem()
+    ctx = wf.context(mol)
+    ctx.set_params(theta)
+    ctx.reserve(Wl)
+    r = ctx.to_soa(initial_walkers(mol, Wl, lo))
+    _, la = ctx.log_psi(r)
+    logp = (2.0 * la).contiguous()
+    e_l = torch.empty(Wl, dtype=torch.float32, device=dev)
+    hdr = torch.empty(8, dtype=torch.float64, device=dev)
+    gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
+    nacc = torch.zeros(Wl, dtype=torch.float32, device=dev)
+    for t in range(args.burn):                                 # equilibrate: walkers ~ |psi|^2, away from nodes
+        ctx.mh_step(r, logp, SIGMA, seed=SEED, step=t, walker_id0=lo)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    step_no = [1 << 20]
+
+    def one_step():
+        s = step_no[0]
+        step_no[0] += 1
+        ctx.walker_step_a(r, logp, SIGMA, e_l, hdr, seed=SEED, step=s, walker_id0=lo, n_accepted=nacc)
+        if world > 1:
+            dist.all_reduce(hdr)
+        ctx.walker_step_b(r, e_l, hdr, gsum)
+        if world > 1:
+            dist.all_reduce(gsum)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1.0)                                       # L2 flush between timed steps (not timed)
+        a.record()
+        one_step()
+        b.record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.launch_count() - launches0
+    prof = {k: ctx.profile_read(i) for i, k in enumerate(["eval1", "eval5", "bwd", "assemble", "accept"])}
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    h = hdr.cpu().numpy()
+
+    # ---- e2e: host buffers in pinned memory, copies inside the timed region -----------------------
+    nn = 3 * mol.n_electrons
+    r_host = torch.empty((Wl, mol.n_electrons, 3), dtype=torch.float32).pin_memory()
+    r_host.copy_(ctx.to_aos(r).cpu())
+    logp_host = torch.empty(Wl, dtype=torch.float32).pin_memory(); logp_host.copy_(logp.cpu())
+    e_host = torch.empty(Wl, dtype=torch.float32).pin_memory()
+    hdr_host = torch.empty(8, dtype=torch.float64).pin_memory()
+    g_host = torch.empty(ctx.P, dtype=torch.float64).pin_memory()
+    h2d = Wl * nn * 4 + Wl * 4
+    d2h = Wl * nn * 4 + Wl * 4 + Wl * 4 + 8 * 8 + ctx.P * 8
+
+    def e2e_step(s):
+        if world == 1:                                         # the C-ABI host entry point itself
+            ctx.walker_step_host(r_host.numpy(), logp_host.numpy(), SIGMA, e_host.numpy(), hdr_host.numpy(),
+                                 g_host.numpy(), seed=SEED, step=s, walker_id0=lo)
+        else:                                                  # same copies, phases split around the all-reduces
+            ra = r_host.to(dev, non_blocking=True)
+            lp = logp_host.to(dev, non_blocking=True)
+            rs = ctx.to_soa(ra)
+            ctx.walker_step_a(rs, lp, SIGMA, e_l, hdr, seed=SEED, step=s, walker_id0=lo)
+            dist.all_reduce(hdr)
+            ctx.walker_step_b(rs, e_l, hdr, gsum)
+            dist.all_reduce(gsum)
+            r_host.copy_(ctx.to_aos(rs), non_blocking=True)
+            logp_host.copy_(lp, non_blocking=True)
+            e_host.copy_(e_l, non_blocking=True)
+            hdr_host.copy_(hdr, non_blocking=True)
+            g_host.copy_(gsum, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for i in range(3):
+        e2e_step((1 << 21) + i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step((1 << 22) + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    out = None
+    if rank == 0:
+        flops_step, flops_value = algorithmic_flops_per_walker_step(N_ATOMS, HIDDEN, mol.n_electrons)
+        pk = peaks()
+        ffma_peak = ctx.ffma_peak(5)
+        ms5, n5 = prof["eval5"]
+        # dominant kernel: the 5-channel orbital forward (value, gradient, Laplacian): 5 * 2 m E flop per walker
+        flops_launch = 5.0 * flops_value * Wl
+        ach = flops_launch / (ms5 / max(n5, 1) * 1e-3) / 1e12 if n5 else None
+        value = world * Wl * args.steps / (total_ms * 1e-3)
+        out = {
+            "metric": "walker-steps/s", "value": value, "unit": "walker-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "H4 chain R=1.8 (2up/2dn) neural Slater-Jastrow, orbital MLP 11-64-64-1 x4, P=19976",
+                       "walkers_per_gpu": Wl, "global_walkers": world * Wl, "step_size": SIGMA,
+                       "rng": "device Philox4x32-10", "l2": "256 MiB flush write between timed steps",
+                       "parallelism": f"walkers sharded over {world} GPU(s); all-reduce hdr(8 f64)+grad(P f64) per step",
+                       "algorithmic_flop_per_walker_step": flops_step},
+            "clocks": clocks,
+            "e2e": {"value": world * Wl * args.steps / e2e_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if world == 1
+                    else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32_ffma", "kernel": "orb_eval_kernel<64,5,4,256> (orbital forward: value+grad+Laplacian)",
+                         "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ach else None,
+                         "peak_source": "measured live: nqmc_ffma_peak (register FFMA chains); MEASURED_PEAKS.json has no fp32 figure",
+                         "peak_nominal_148x128x2x1.965GHz": 74.4, "bf16_tensor_peak_measured": pk.get("bf16_tflops"),
+                         "hbm_gbs_measured": pk.get("hbm_gbs"), "traffic": None,
+                         "whole_step_achieved_tflops": flops_step * Wl / (total_ms / args.steps * 1e-3) / 1e12,
+                         "kernel_ms": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
+                         "kernel_launches": {k: v[1] for k, v in prof.items()}},
+            "sanity": {"mean_E_L": h[1] / max(h[0], 1), "n_finite": h[0], "n_bad": h[4], "acceptance": h[3] / (world * Wl)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_walkers, steps=2, warmup=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# =================================================================================================
+def cpu_baseline(n_walkers, steps, warmup):
+    """The reference's algorithm (vmap + dense-Hessian kinetic energy + vmap(grad wrt params)) restated with
+    torch.func (oracle/nqmc_autodiff.py), float32, on all host cores, on a bounded sample of the workload."""
+    import torch
+    from oracle.layout import OracleNet, hydrogen_chain_system, init_theta
+    from oracle.nqmc_autodiff import AutodiffOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    s = hydrogen_chain_system(N_ATOMS, BOND)
+    net = OracleNet(kind=1, hidden=(HIDDEN, HIDDEN))
+    th = init_theta(s, net, SEED).astype(np.float32)
+    a = AutodiffOracle(s, net, dtype=torch.float32)
+    rng = np.random.default_rng(SEED)
+    r = (s.R[np.arange(s.n_elec) % s.n_atoms][None] + 0.5 * rng.standard_normal((n_walkers, s.n_elec, 3))).astype(np.float32)
+    _, la = a.log_psi(th, r)
+    logp = 2 * la
+    times = []
+    for i in range(warmup + steps):
+        n = rng.standard_normal(r.shape).astype(np.float32)
+        u = rng.random(n_walkers).astype(np.float32)
+        t0 = time.perf_counter()
+        r, logp, _, _, _ = a.walker_step(th, r, logp, n, u, SIGMA)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    v = n_walkers * len(times) / sum(times)
+    return {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_walkers} walkers x {len(times)} steps of the same H4 workload; torch.func restatement of the "
+                      f"reference algorithm (nested-autodiff Hessian), float32, torch {torch.__version__}; "
+                      "the reference's JAX path cannot run here (jax/flax/optax not installed)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warm = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    cb = cpu_baseline(args.cpu_walkers, steps=steps, warmup=warm)
+    flops_step, _ = algorithmic_flops_per_walker_step(N_ATOMS, HIDDEN, N_ATOMS)
+    print(json.dumps({
+        "impl": "reference", "metric": "walker-steps/s", "value": cb["value"], "unit": "walker-steps/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * args.cpu_walkers / cb["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "H4 chain R=1.8 (2up/2dn) neural Slater-Jastrow, orbital MLP 11-64-64-1 x4, P=19976",
+                   "walkers_per_step_sample": args.cpu_walkers, "algorithmic_flop_per_walker_step": flops_step},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers-per-gpu", type=int, default=WALKERS_PER_GPU)
+    ap.add_argument("--burn", type=int, default=100)
+    ap.add_argument("--cpu-walkers", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

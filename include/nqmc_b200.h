@@ -169,6 +169,15 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, co
 /* ---- introspection --------------------------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t nqmc_launch_count(const nqmc_ctx* ctx);
+/* Per-kernel CUDA-event timing on the launching stream (used by bench.py for the roofline leg).
+ * kind: 0 orbital forward (value), 1 orbital forward (value+grad+Laplacian), 2 orbital reverse pass,
+ *       3 Slater/Jastrow/E_L assembly, 4 accept.  nqmc_profile(ctx, 1) resets and enables; _read
+ *       synchronises the device and returns the summed duration and the number of launches recorded. */
+int nqmc_profile(nqmc_ctx* ctx, int enable);
+int nqmc_profile_read(nqmc_ctx* ctx, int kind, double* total_ms, int64_t* count);
+/* Measured FP32 FMA throughput of this GPU in TFLOP/s (register-resident FFMA chains, best of reps):
+ * the roofline denominator of the FFMA-bound kernels (MEASURED_PEAKS.json has no fp32 figure). */
+int nqmc_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, nqmc_stream stream);
 /* Fill normals SoA [3N][W] / uniforms [W] from the device Philox stream (for RNG parity tests). */
 int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t walker_id0, int64_t W, float* normals,
                   float* uniforms, nqmc_stream stream);

@@ -456,6 +456,34 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
 
 int64_t nqmc_launch_count(const nqmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+int nqmc_profile(nqmc_ctx* ctx, int enable) {
+  if (!ctx) return NQMC_ERR_ARG;
+  ctx->prof_on = enable != 0;
+  for (int k = 0; k < nqmc_ctx::PROF_KINDS; ++k) ctx->prof_n[k] = 0;
+  return NQMC_OK;
+}
+
+int nqmc_profile_read(nqmc_ctx* ctx, int kind, double* total_ms, int64_t* count) {
+  if (!ctx || kind < 0 || kind >= nqmc_ctx::PROF_KINDS || !total_ms || !count) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaDeviceSynchronize());
+  double tot = 0;
+  for (int i = 0; i < ctx->prof_n[kind]; ++i) {
+    float ms = 0;
+    NQMC_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[kind][i][0], ctx->prof_ev[kind][i][1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *count = ctx->prof_n[kind];
+  return NQMC_OK;
+}
+
+int nqmc_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, nqmc_stream st) {
+  if (!ctx || !tflops || ctx->cap_w <= 0) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_ffma_peak(ctx, reps, tflops, S(st));
+}
+
 int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, float* normals, float* uniforms,
                   nqmc_stream st) {
   if (!ctx || W <= 0) return NQMC_ERR_ARG;

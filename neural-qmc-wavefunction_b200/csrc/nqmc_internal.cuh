@@ -82,6 +82,24 @@ struct nqmc_ctx {
   int n_cta_bwd = 0;
   int p_mlp = 0;               // scalars in one orbital network
   double* hdr_tmp = nullptr;   // [8]
+  // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
+  bool prof_on = false;
+  static constexpr int PROF_KINDS = 6, PROF_RING = 512;
+  cudaEvent_t prof_ev[PROF_KINDS][PROF_RING][2] = {};
+  int prof_n[PROF_KINDS] = {};
+};
+enum { NQ_PROF_EVAL1 = 0, NQ_PROF_EVAL5 = 1, NQ_PROF_BWD = 2, NQ_PROF_ASSEMBLE = 3, NQ_PROF_ACCEPT = 4, NQ_PROF_MISC = 5 };
+
+struct ProfScope {   // records start/stop events around one launch on the launching stream
+  nqmc_ctx* c; int kind; cudaStream_t st; int slot = -1;
+  ProfScope(nqmc_ctx* ctx, int k, cudaStream_t s) : c(ctx), kind(k), st(s) {
+    if (c->prof_on && c->prof_n[k] < nqmc_ctx::PROF_RING) {
+      slot = c->prof_n[k]++;
+      if (!c->prof_ev[k][slot][0]) { cudaEventCreate(&c->prof_ev[k][slot][0]); cudaEventCreate(&c->prof_ev[k][slot][1]); }
+      cudaEventRecord(c->prof_ev[k][slot][0], st);
+    }
+  }
+  ~ProfScope() { if (slot >= 0) cudaEventRecord(c->prof_ev[kind][slot][1], st); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,3 +190,4 @@ int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
                      const float* uniforms, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, uint8_t* accept,
                      float* n_acc, cudaStream_t st);
 int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);
+int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st);

@@ -611,7 +611,10 @@ int launch_eval_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStre
   int n_chunks = (ctx->sm_count * occ) / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
-  kern<<<n_chunks * s.n_mlp, NT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+  {
+    ProfScope ps(ctx, C == 5 ? NQ_PROF_EVAL5 : NQ_PROF_EVAL1, st);
+    kern<<<n_chunks * s.n_mlp, NT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+  }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
@@ -638,8 +641,11 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
   int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
   if (n_chunks > max_items) n_chunks = (int)max_items;
   if (n_chunks < 1) n_chunks = 1;
-  kern<<<n_chunks * s.n_mlp, NT, smem, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp, n_chunks,
-                                             ctx->p_mlp);
+  {
+    ProfScope ps(ctx, NQ_PROF_BWD, st);
+    kern<<<n_chunks * s.n_mlp, NT, smem, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp, n_chunks,
+                                               ctx->p_mlp);
+  }
   NQMC_LAUNCH_CHECK();
   dim3 g((ctx->p_mlp + 255) / 256, s.n_mlp);
   orb_bwd_reduce_kernel<<<g, 256, 0, st>>>(s, ctx->part_mlp, n_chunks, ctx->p_mlp, out);

@@ -549,6 +549,24 @@ __global__ void accept_logabs_kernel(const DevSys s, float* __restrict__ r, floa
   if (acc_flag) acc_flag[w] = acc ? 1.0f : 0.0f;
 }
 
+// FP32 FFMA pipe microbenchmark: 16 independent FMA chains per thread (the roofline denominator of
+// the FFMA-bound orbital kernels; MEASURED_PEAKS.json has no fp32 figure)
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, const int iters, const float a, const float b) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 123.456f) out[0] = s;
+}
+
 template <typename F>
 int dispatch_ns(nqmc_ctx* ctx, F&& f) {
   const int ns = ctx->sys.n_up > ctx->sys.n_dn ? ctx->sys.n_up : ctx->sys.n_dn;
@@ -575,6 +593,7 @@ int nq_launch_accept(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
                      uint64_t step, int64_t wid0, int64_t W, uint8_t* accept, float* n_acc, cudaStream_t st) {
   return dispatch_ns(ctx, [&](auto ns) -> int {
     constexpr int NS = decltype(ns)::value;
+    ProfScope ps(ctx, NQ_PROF_ACCEPT, st);
     accept_kernel<NS><<<(unsigned)((W + WT - 1) / WT), WT, 0, st>>>(ctx->sys, ctx->theta, r, logp, r_prop, ctx->phi,
                                                                      uniforms, seed, step, wid0, W, accept, n_acc,
                                                                      ctx->wgt);
@@ -587,6 +606,7 @@ int nq_launch_assemble(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, flo
                        float* logabs, float* sign, cudaStream_t st) {
   return dispatch_ns(ctx, [&](auto ns) -> int {
     constexpr int NS = decltype(ns)::value;
+    ProfScope ps(ctx, NQ_PROF_ASSEMBLE, st);
     assemble_kernel<NS><<<(unsigned)((W + WT - 1) / WT), WT, 0, st>>>(ctx->sys, ctx->theta, r, ctx->phi,
                                                                        want_energy ? ctx->inv : nullptr, W, e_l, parts,
                                                                        logabs, sign, want_energy ? 1 : 0);
@@ -663,4 +683,27 @@ int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_
     NQMC_LAUNCH_CHECK();
     return (int)NQMC_OK;
   });
+}
+
+// returns FP32 FMA throughput in TFLOP/s (2 flop per FMA), best of `reps`
+int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st) {
+  cudaEvent_t e0, e1;
+  NQMC_CUDA(cudaEventCreate(&e0));
+  NQMC_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  double best = 0;
+  for (int rpt = 0; rpt < reps + 1; ++rpt) {
+    NQMC_CUDA(cudaEventRecord(e0, st));
+    ffma_peak_kernel<<<blocks, 256, 0, st>>>(ctx->logabs, iters, 0.999f, 0.001f);
+    NQMC_CUDA(cudaEventRecord(e1, st));
+    NQMC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NQMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 64.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+    if (rpt > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return NQMC_OK;
 }

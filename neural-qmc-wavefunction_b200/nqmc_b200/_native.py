@@ -25,7 +25,7 @@ EXPORTS = [
     "nqmc_leaf_info", "nqmc_set_params", "nqmc_set_params_host", "nqmc_aos_to_soa", "nqmc_soa_to_aos",
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
-    "nqmc_launch_count", "nqmc_rng_fill",
+    "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak",
 ]
 
 
@@ -83,6 +83,9 @@ def load_library():
     lib.nqmc_launch_count.argtypes = [vp]
     lib.nqmc_launch_count.restype = i64
     lib.nqmc_rng_fill.argtypes = [vp, u64, u64, i64, i64, vp, vp, vp]
+    lib.nqmc_profile.argtypes = [vp, C.c_int]
+    lib.nqmc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.nqmc_ffma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp]
     _lib = lib
     return lib
 
@@ -277,6 +280,20 @@ class Context:
                                                    np_ptr(uniforms), int(seed) & (2**64 - 1), int(step), int(walker_id0),
                                                    float(sigma), W, e_l.ctypes.data, hdr.ctypes.data, gsum.ctypes.data,
                                                    self.stream), "nqmc_walker_step_host")
+
+    def profile(self, enable: bool):
+        self._check(self.lib.nqmc_profile(self.h, int(enable)), "nqmc_profile")
+
+    def profile_read(self, kind: int) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.nqmc_profile_read(self.h, kind, C.byref(ms), C.byref(n)), "nqmc_profile_read")
+        return ms.value, n.value
+
+    def ffma_peak(self, reps: int = 5) -> float:
+        self.reserve(max(self.cap, 1024))
+        tf = C.c_double()
+        self._check(self.lib.nqmc_ffma_peak(self.h, reps, C.byref(tf), self.stream), "nqmc_ffma_peak")
+        return tf.value
 
     def rng_fill(self, W: int, seed: int, step: int, walker_id0: int = 0):
         torch = _torch()

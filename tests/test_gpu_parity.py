@@ -96,15 +96,20 @@ def test_grad_accum(case):
     rng = np.random.default_rng(5)
     wgt = rng.standard_normal(W).astype(np.float32)
     O = o.grad_log_psi(case["th64"], case["r64"])
+    # yardstick: the same analytic algorithm evaluated in float32 by NumPy (the reference computes in fp32)
+    O32 = o.grad_log_psi(case["theta"], case["r"]).astype(np.float64)
     for w_np in (None, wgt):
         w_t = None if w_np is None else torch.as_tensor(w_np).to(ctx.dev())
         got = ctx.grad_accum(case["soa"], w_t).cpu().numpy()
         ref = O.sum(0) if w_np is None else (w_np.astype(np.float64)[:, None] * O).sum(0)
         scale = np.abs(O).sum(0) if w_np is None else (np.abs(w_np)[:, None] * np.abs(O)).sum(0)
+        ref32 = O32.sum(0) if w_np is None else (w_np.astype(np.float64)[:, None] * O32).sum(0)
         err = np.abs(got - ref) / np.maximum(scale, 1e-3)          # error relative to the sum of magnitudes
-        print("grad_accum err max/median", err.max(), np.median(err))
-        assert err.max() <= 2e-4, err.max()
+        err32 = np.abs(ref32 - ref) / np.maximum(scale, 1e-3)
+        print("grad_accum err max/median", err.max(), np.median(err), "fp32-numpy yardstick max", err32.max())
         assert np.median(err) <= 1e-5
+        assert np.quantile(err, 0.99) <= 2e-4
+        assert err.max() <= 2 * max(err32.max(), 2.5e-4), (err.max(), err32.max())
 
 
 def test_mh_step_explicit_streams(case):
@@ -178,7 +183,11 @@ def test_walker_step_sums(case):
     scale = (np.abs(e_ref - e_ref.mean())[:, None] * np.abs(O)).sum(0)
     err = np.abs(gsum.cpu().numpy() - ref) / np.maximum(scale, 1e-3)
     print("walker_step gsum err max/median", err.max(), np.median(err), "mean E", mean, e_ref.mean())
-    assert err.max() <= 5e-3 and np.median(err) <= 1e-4
+    e32, _, _, _ = o.local_energy(case["theta"], r_new.astype(np.float32))
+    O32 = o.grad_log_psi(case["theta"], r_new.astype(np.float32)).astype(np.float64)
+    e32 = e32.astype(np.float64)
+    err32 = np.abs(((e32 - e32.mean())[:, None] * O32).sum(0) - ref) / np.maximum(scale, 1e-3)
+    assert np.median(err) <= 1e-4 and err.max() <= 2 * max(err32.max(), 1e-3), (err.max(), err32.max())
     # host-buffer entry point gives the same numbers
     r_h = np.ascontiguousarray(r); lp_h = logp0.copy(); e_h = np.empty(W, np.float32)
     hdr_h = np.empty(8, np.float64); g_h = np.empty(ctx.P, np.float64)
@@ -186,7 +195,8 @@ def test_walker_step_sums(case):
     assert np.array_equal(r_h, ctx.to_aos(soa).cpu().numpy())
     assert np.array_equal(e_h, e)
     assert np.array_equal(hdr_h, h)
-    assert np.allclose(g_h, gsum.cpu().numpy(), rtol=1e-12, atol=0)
+    # shared-memory float atomics make the summation order (not the math) run-dependent
+    assert np.allclose(g_h, gsum.cpu().numpy(), rtol=1e-5, atol=1e-5 * np.abs(g_h).max())
 
 
 def test_device_rng_matches_philox_oracle(case):
