@@ -293,17 +293,23 @@ struct BCfg {
   static constexpr int SH = H + 4;           // stride of [row][k] arrays
   static constexpr int KPT = H / RG;         // k's per thread in the dW2 outer product
   static constexpr int FG = NT / H;          // feature groups in the dW1 product
-  static_assert(H % RG == 0 && KPT % 4 == 0 || KPT == 1 || KPT == 2, "");
+  static constexpr int A1SZ = (H * SR > TR * SH) ? H * SR : TR * SH;   // A1 ([H][SR]) is later reused as D1r ([TR][SH])
+  static_assert(H % RG == 0, "row groups must divide the hidden width");
+  static_assert(KPT == 1 || KPT == 2 || KPT % 4 == 0, "k's per thread");
+  static size_t smem_floats(int F) {
+    return (size_t)F * H + 2 * (size_t)H * H + 3 * H + (size_t)F * SR + A1SZ + 2 * (size_t)TR * SH + (size_t)H * SR + TR +
+           4 * H + 4;
+  }
 };
 
 template <int H, int NT>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
     orb_bwd_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r,
                    const float* __restrict__ inv, const float* __restrict__ wgt, const double* __restrict__ hdr,
                    const float* __restrict__ e_l, const int64_t W, float* __restrict__ part, const int n_chunks,
                    const int p_mlp) {
   using K = BCfg<H, NT>;
-  constexpr int CG = K::CG, RG = K::RG, TR = K::TR, SR = K::SR, SH = K::SH, KPT = K::KPT, FG = K::FG;
+  constexpr int CG = K::CG, TR = K::TR, SR = K::SR, SH = K::SH, KPT = K::KPT, FG = K::FG;
   constexpr int MAXFF = (35 + FG - 1) / FG;
   extern __shared__ __align__(16) float smem[];
   const int F = s.F;
@@ -314,12 +320,12 @@ __global__ void __launch_bounds__(NT, 1)
   float* b2p = b1p + H;
   float* W3p = b2p + H;
   float* Fs = W3p + H;               // [F][SR]   features (value only)
-  float* A1 = Fs + 36 * SR;          // [H][SR]   h1 as [k][row]   (layer-2 operand)
-  float* H1r = A1 + H * SR;          // [TR][SH]  h1 as [row][p]
+  float* A1 = Fs + F * SR;           // [H][SR]   h1 as [k][row]   (layer-2 operand) ...
+  float* D1r = A1;                   // [TR][SH]  ... reused for delta1 as [row][p] once layer 2 is done
+  float* H1r = A1 + K::A1SZ;         // [TR][SH]  h1 as [row][p]
   float* D2r = H1r + TR * SH;        // [TR][SH]  delta2 as [row][q]
   float* D2T = D2r + TR * SH;        // [H][SR]   delta2 as [q][row]
-  float* D1r = D2T + H * SR;         // [TR][SH]  delta1 as [row][p]
-  float* seedS = D1r + TR * SH;      // [TR]
+  float* seedS = D2T + H * SR;       // [TR]
   float* redS = seedS + TR;          // [4*H + 4] bias / W3 partial reduction
 
   const int tid = threadIdx.x;
@@ -337,8 +343,7 @@ __global__ void __launch_bounds__(NT, 1)
   }
   for (int idx = tid; idx < H * H; idx += NT) {
     int k = idx / H, q = idx % H;
-    float v = theta[off.W2 + k * H + perm_col(q, CG)];
-    W2p[idx] = v;
+    W2p[idx] = theta[off.W2 + k * H + perm_col(q, CG)];
   }
   for (int idx = tid; idx < H * H; idx += NT) {
     int q = idx / H, p = idx % H;
@@ -351,15 +356,12 @@ __global__ void __launch_bounds__(NT, 1)
     W3p[q] = theta[off.W3 + j];
   }
   for (int q = tid; q < 4 * H + 4; q += NT) redS[q] = 0.f;
-  const float b3 = theta[off.b3];
-  (void)b3;
-  double center = 0.0;
-  if (hdr != nullptr) center = hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0);
-  const float centerf = (float)center;
+  float centerf = 0.f;
+  if (hdr != nullptr) centerf = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
   __syncthreads();
 
   // persistent accumulators
-  float gW2[KPT][4];       // dW2[p = kgrp*KPT + kk][q = 4*cg + jj]   (thread (rg as kgrp, cg))
+  float gW2[KPT][4];       // dW2[p = rg*KPT + kk][q = 4*cg + jj]
 #pragma unroll
   for (int kk = 0; kk < KPT; ++kk)
 #pragma unroll
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1)
       for (int jj = 0; jj < 4; ++jj)
         *reinterpret_cast<float4*>(D2T + (4 * cg + jj) * SR + 4 * rg) = make_float4(h2[0][jj], h2[1][jj], h2[2][jj], h2[3][jj]);
     }
-    __syncthreads();
+    __syncthreads();   // A1 is dead from here on (D1r reuses it)
     // ---- delta1 = (delta2 W2^T) * (1 - h1^2)   thread: rows 4rg.., p = 4cg.. ----------------
     {
       float d1[4][4];
@@ -522,13 +524,17 @@ __global__ void __launch_bounds__(NT, 1)
     // ---- dW1[f][p] += sum_rows f[row] * delta1[row][p] ; db1[p] += sum_rows delta1 ------------
     {
       const int p = tid % H, fg = tid / H;
-      for (int row = 0; row < TR; ++row) {
-        const float dv = D1r[row * SH + p];
-        if (fg == 0) gb1 += dv;
+      for (int row = 0; row < TR; row += 4) {
+        const float dv0 = D1r[(row + 0) * SH + p], dv1 = D1r[(row + 1) * SH + p], dv2 = D1r[(row + 2) * SH + p],
+                    dv3 = D1r[(row + 3) * SH + p];
+        if (fg == 0) gb1 += (dv0 + dv1) + (dv2 + dv3);
 #pragma unroll
         for (int ff = 0; ff < MAXFF; ++ff) {
           const int f = fg + FG * ff;
-          if (f < F) gW1[ff] = fmaf(Fs[f * SR + row], dv, gW1[ff]);
+          if (f < F) {
+            const float4 fv = *reinterpret_cast<const float4*>(Fs + f * SR + row);
+            gW1[ff] = fmaf(fv.x, dv0, fmaf(fv.y, dv1, fmaf(fv.z, dv2, fmaf(fv.w, dv3, gW1[ff]))));
+          }
         }
       }
     }
@@ -568,15 +574,25 @@ __global__ void __launch_bounds__(NT, 1)
   if (tid == 0) slab[o_b3] = redS[2 * H];
 }
 
-// reduce per-CTA slabs of every network into the fp64 output (theta order)
+// reduce per-CTA slabs of every network into the fp64 output (theta order): one warp per group of
+// 32 consecutive slab entries would be coalesced already; here each thread owns one entry and the
+// chunk loop is unrolled by 4 for memory-level parallelism.
 __global__ void orb_bwd_reduce_kernel(const DevSys s, const float* __restrict__ part, const int n_chunks, const int p_mlp,
                                       double* __restrict__ out) {
   const int m = blockIdx.y;
   const MlpOff off = s.mlp[m];
   const int H = s.H, F = s.F;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p_mlp; idx += gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int c = 0; c < n_chunks; ++c) acc += (double)part[(int64_t)(c * s.n_mlp + m) * p_mlp + idx];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 3 < n_chunks; c += 4) {
+      a0 += (double)part[(int64_t)((c + 0) * s.n_mlp + m) * p_mlp + idx];
+      a1 += (double)part[(int64_t)((c + 1) * s.n_mlp + m) * p_mlp + idx];
+      a2 += (double)part[(int64_t)((c + 2) * s.n_mlp + m) * p_mlp + idx];
+      a3 += (double)part[(int64_t)((c + 3) * s.n_mlp + m) * p_mlp + idx];
+    }
+    for (; c < n_chunks; ++c) a0 += (double)part[(int64_t)(c * s.n_mlp + m) * p_mlp + idx];
+    const double acc = (a0 + a1) + (a2 + a3);
     // slab order: b1[H] W1[F*H] b2[H] W2[H*H] b3 W3[H]
     int o;
     if (idx < H) o = off.b1 + idx;
@@ -624,8 +640,7 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
                  double* out, cudaStream_t st) {
   using K = BCfg<H, NT>;
   const DevSys& s = ctx->sys;
-  size_t smem = sizeof(float) * ((size_t)s.F * H + 2 * (size_t)H * H + 3 * H + 36 * K::SR + 2 * (size_t)H * K::SR +
-                                 3 * (size_t)K::TR * K::SH + K::TR + 4 * H + 4);
+  size_t smem = sizeof(float) * K::smem_floats(s.F);
   auto kern = orb_bwd_kernel<H, NT>;
   static bool configured = false;
   if (!configured) {
@@ -636,7 +651,12 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
     ctx->err = "orb_bwd: configuration does not fit in shared memory";
     return NQMC_ERR_UNSUPPORTED;
   }
-  int n_chunks = ctx->n_cta_bwd / s.n_mlp;
+  int occ = 1;
+  NQMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  if (occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  int n_chunks = (ctx->sm_count * occ) / s.n_mlp;
+  if (n_chunks * s.n_mlp > ctx->n_cta_bwd) n_chunks = ctx->n_cta_bwd / s.n_mlp;
   const int64_t nwb = (W + K::TR - 1) / K::TR;
   int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
   if (n_chunks > max_items) n_chunks = (int)max_items;
@@ -675,7 +695,7 @@ int nq_launch_orb_bwd(nqmc_ctx* ctx, const float* r, const float* wgt, const dou
   const int H = ctx->sys.H;
   if (H == 32) return launch_bwd_t<32, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);
   if (H == 64) return launch_bwd_t<64, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);
-  if (H == 128) return launch_bwd_t<128, 512>(ctx, r, wgt, hdr_center, e_l, W, out, st);
+  if (H == 128) return launch_bwd_t<128, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);
   ctx->err = "orb_bwd: unsupported hidden width";
   return NQMC_ERR_UNSUPPORTED;
 }

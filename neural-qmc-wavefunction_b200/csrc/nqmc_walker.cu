@@ -374,12 +374,13 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
   }
 }
 __global__ void stats_finish_kernel(const double* __restrict__ part, const int nblk, double* __restrict__ hdr) {
-  if (threadIdx.x < NQMC_HDR_SIZE) {
-    double a = 0;
-    if (threadIdx.x < 5)
-      for (int b = 0; b < nblk; ++b) a += part[(int64_t)b * NPART + threadIdx.x];
-    hdr[threadIdx.x] = a;
-  }
+  // one warp per header slot; lanes stride the block partials (fixed order => deterministic)
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0;
+  if (slot < 5)
+    for (int b = lane; b < nblk; b += 32) a += part[(int64_t)b * NPART + slot];
+  a = warp_sum(a);
+  if (lane == 0 && slot < NQMC_HDR_SIZE) hdr[slot] = slot < 5 ? a : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -469,10 +470,13 @@ __global__ void __launch_bounds__(WT) walker_grads_kernel(const DevSys s, const 
 
 __global__ void walker_grads_finish_kernel(const DevSys s, const double* __restrict__ part, const int nblk,
                                            const int n_slots, double* __restrict__ out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per slot; lanes stride the block partials
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= n_slots) return;
   double a = 0;
-  for (int b = 0; b < nblk; ++b) a += part[(int64_t)b * n_slots + q];
+  for (int b = lane; b < nblk; b += 32) a += part[(int64_t)b * n_slots + q];
+  a = warp_sum(a);
+  if (lane != 0) return;
   int o = -1;
   if (q == 0) o = s.jas_a_ee;
   else if (q == 1) o = s.jas_a_en;
@@ -621,7 +625,7 @@ int nq_launch_stats(nqmc_ctx* ctx, const float* e_l, const float* acc_flag, int6
   if (nblk < 1) nblk = 1;
   stats_partial_kernel<<<nblk, 256, 0, st>>>(e_l, acc_flag, W, ctx->part_walk);
   NQMC_LAUNCH_CHECK();
-  stats_finish_kernel<<<1, 32, 0, st>>>(ctx->part_walk, nblk, hdr);
+  stats_finish_kernel<<<1, 32 * NQMC_HDR_SIZE, 0, st>>>(ctx->part_walk, nblk, hdr);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
@@ -638,7 +642,7 @@ int nq_launch_walker_grads(nqmc_ctx* ctx, const float* r, const float* wgt, cons
   walker_grads_kernel<<<nblk, WT, n_slots * sizeof(float), st>>>(s, ctx->theta, r, wgt, hdr_center, e_l, W,
                                                                  ctx->part_walk, n_slots);
   NQMC_LAUNCH_CHECK();
-  walker_grads_finish_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(s, ctx->part_walk, nblk, n_slots, out);
+  walker_grads_finish_kernel<<<(n_slots * 32 + 127) / 128, 128, 0, st>>>(s, ctx->part_walk, nblk, n_slots, out);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
