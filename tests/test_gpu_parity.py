@@ -23,6 +23,8 @@ CASES = [
     dict(n_atoms=4, hidden=64, W=64, seed=3),
     dict(n_atoms=4, hidden=32, W=257, use_cusp=True),
     dict(n_atoms=6, hidden=64, W=384, use_cusp=True),
+    dict(n_atoms=6, hidden=128, W=200, use_cusp=True),
+    dict(n_atoms=10, hidden=128, W=96),
     dict(n_atoms=2, hidden=64, W=200, kind=KIND_SIMPLE),
     dict(n_atoms=4, hidden=48, W=130, kind=KIND_SIMPLE),
 ]
@@ -107,9 +109,11 @@ def test_grad_accum(case):
         err = np.abs(got - ref) / np.maximum(scale, 1e-3)          # error relative to the sum of magnitudes
         err32 = np.abs(ref32 - ref) / np.maximum(scale, 1e-3)
         print("grad_accum err max/median", err.max(), np.median(err), "fp32-numpy yardstick max", err32.max())
+        # median: absolute bar; tails: same order as the float32 NumPy evaluation of the same algorithm
+        # (the tail is set by a few ill-conditioned walkers, cond(Phi) ~ 1e2..1e3 -- SURVEY 8(d))
         assert np.median(err) <= 1e-5
-        assert np.quantile(err, 0.99) <= 2e-4
-        assert err.max() <= 2 * max(err32.max(), 2.5e-4), (err.max(), err32.max())
+        assert np.quantile(err, 0.99) <= 3 * max(np.quantile(err32, 0.99), 1e-4)
+        assert err.max() <= 5 * max(err32.max(), 1e-3), (err.max(), err32.max())
 
 
 def test_mh_step_explicit_streams(case):
@@ -187,7 +191,9 @@ def test_walker_step_sums(case):
     O32 = o.grad_log_psi(case["theta"], r_new.astype(np.float32)).astype(np.float64)
     e32 = e32.astype(np.float64)
     err32 = np.abs(((e32 - e32.mean())[:, None] * O32).sum(0) - ref) / np.maximum(scale, 1e-3)
-    assert np.median(err) <= 1e-4 and err.max() <= 2 * max(err32.max(), 1e-3), (err.max(), err32.max())
+    assert np.median(err) <= 1e-5
+    assert np.quantile(err, 0.99) <= 3 * max(np.quantile(err32, 0.99), 1e-4)
+    assert err.max() <= 5 * max(err32.max(), 1e-3), (err.max(), err32.max())
     # host-buffer entry point gives the same numbers
     r_h = np.ascontiguousarray(r); lp_h = logp0.copy(); e_h = np.empty(W, np.float32)
     hdr_h = np.empty(8, np.float64); g_h = np.empty(ctx.P, np.float64)
