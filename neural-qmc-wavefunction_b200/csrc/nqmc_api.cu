@@ -43,7 +43,7 @@ void build_param_map(nqmc_ctx* ctx) {
     s.P = (int)lb.off;
     return;
   }
-  if (s.use_bf) s.bf = lb.mlp3("params/backflow", 2, NQMC_BF_H);
+  if (ctx->want_bf) s.bf = lb.mlp3("params/backflow", 2, NQMC_BF_H);
   if (s.use_cusp) {
     s.ee_cusp_b = lb.add("params/ee_cusp/b_ee", 1, 1);
     std::vector<std::pair<std::string, int>> names;
@@ -81,11 +81,12 @@ int check_w(nqmc_ctx* ctx, int64_t W) {
 }
 
 void free_scratch(nqmc_ctx* c) {
-  void* ptrs[] = {c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
+  void* ptrs[] = {c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
                   c->part_mlp, c->hdr_tmp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  c->x_cur = c->x_prop = c->vvec = nullptr;
   c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = nullptr;
@@ -134,10 +135,6 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
       g_create_err = "3 + 2*n_atoms orbital features must not exceed the hidden width";
       return NQMC_ERR_UNSUPPORTED;
     }
-    if (net->use_backflow) {
-      g_create_err = "backflow is not implemented yet in this build";
-      return NQMC_ERR_UNSUPPORTED;
-    }
   } else if (net->hidden0 < 1 || net->hidden0 > 128) {
     g_create_err = "SimpleWavefunction hidden width must be in 1..128";
     return NQMC_ERR_UNSUPPORTED;
@@ -179,7 +176,7 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
   s.kind = net->kind;
   s.H = net->hidden0;
   s.use_cusp = net->kind == NQMC_KIND_ANTISYMMETRIC ? (net->use_cusp != 0) : 0;
-  s.use_bf = 0;
+  s.use_bf = net->kind == NQMC_KIND_ANTISYMMETRIC ? (net->use_backflow != 0 && sys->n_elec >= 2) : 0;
   s.F = net->kind == NQMC_KIND_ANTISYMMETRIC ? 3 + 2 * s.A : 3 * s.N;
   s.n_mlp = s.n_up + s.n_dn;
   s.n_ent = s.n_up * s.n_up + s.n_dn * s.n_dn;
@@ -191,6 +188,7 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
     for (int d = 0; d < 3; ++d) s.R[3 * a + d] = (float)sys->R[3 * a + d];
     s.Z[a] = (float)sys->Z[a];
   }
+  ctx->want_bf = net->kind == NQMC_KIND_ANTISYMMETRIC && net->use_backflow != 0;
   build_param_map(ctx);
   ctx->p_mlp = s.kind == NQMC_KIND_ANTISYMMETRIC ? (s.F * s.H + s.H + s.H * s.H + s.H + s.H + 1) : s.P;
   e = cudaMalloc(&ctx->theta, sizeof(float) * (size_t)s.P);
@@ -222,7 +220,12 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   const size_t nn = 3 * (size_t)s.N, w = (size_t)W, f = sizeof(float);
   const size_t n_ent = s.n_ent > 0 ? s.n_ent : 1;
   NQMC_CUDA(cudaMalloc(&ctx->r_prop, nn * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->phi, 5 * n_ent * w * f));
+  NQMC_CUDA(cudaMalloc(&ctx->phi, (s.use_bf ? 10 : 5) * n_ent * w * f));
+  if (s.use_bf) {
+    NQMC_CUDA(cudaMalloc(&ctx->x_cur, nn * w * f));
+    NQMC_CUDA(cudaMalloc(&ctx->x_prop, nn * w * f));
+    NQMC_CUDA(cudaMalloc(&ctx->vvec, nn * w * f));
+  }
   NQMC_CUDA(cudaMalloc(&ctx->inv, n_ent * w * f));
   NQMC_CUDA(cudaMalloc(&ctx->logabs, w * f));
   NQMC_CUDA(cudaMalloc(&ctx->sign, w * f));
@@ -308,7 +311,13 @@ int nqmc_log_psi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, float*
     if (sign) rc = nq_fill(ctx, sign, 1.0f, W, S(st));   // psi = exp(real) > 0
     return rc;
   }
-  rc = nq_launch_orb_eval(ctx, r, W, 1, ctx->phi, S(st));
+  const float* pos = r;
+  if (ctx->sys.use_bf) {
+    rc = nq_launch_backflow_x(ctx, r, W, ctx->x_cur, S(st));
+    if (rc) return rc;
+    pos = ctx->x_cur;
+  }
+  rc = nq_launch_orb_eval(ctx, pos, W, 1, ctx->phi, S(st));
   if (rc) return rc;
   return nq_launch_assemble(ctx, r, W, nullptr, nullptr, false, logabs, sign, S(st));
 }
@@ -323,7 +332,13 @@ static int mh_core(nqmc_ctx* ctx, float* r, float* logp, const float* normals, c
     if (rc) return rc;
     return nq_accept_logabs(ctx, r, logp, ctx->r_prop, ctx->logabs, uniforms, seed, step, wid0, W, accept, n_acc, st);
   }
-  rc = nq_launch_orb_eval(ctx, ctx->r_prop, W, 1, ctx->phi, st);
+  const float* pos = ctx->r_prop;
+  if (ctx->sys.use_bf) {
+    rc = nq_launch_backflow_x(ctx, ctx->r_prop, W, ctx->x_prop, st);
+    if (rc) return rc;
+    pos = ctx->x_prop;
+  }
+  rc = nq_launch_orb_eval(ctx, pos, W, 1, ctx->phi, st);
   if (rc) return rc;
   return nq_launch_accept(ctx, r, logp, ctx->r_prop, uniforms, seed, step, wid0, W, accept, n_acc, st);
 }
@@ -339,6 +354,13 @@ int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, con
 
 static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
+  if (ctx->sys.use_bf) {
+    int rc = nq_launch_backflow_x(ctx, r, W, ctx->x_cur, st);
+    if (rc) return rc;
+    rc = nq_launch_orb_eval(ctx, ctx->x_cur, W, 10, ctx->phi, st);
+    if (rc) return rc;
+    return nq_launch_assemble_bf(ctx, r, W, e_l, parts, st);
+  }
   int rc = nq_launch_orb_eval(ctx, r, W, 5, ctx->phi, st);
   if (rc) return rc;
   return nq_launch_assemble(ctx, r, W, e_l, parts, true, nullptr, nullptr, st);
@@ -357,9 +379,12 @@ static int grads_core(nqmc_ctx* ctx, const float* r, const float* wgt, const dou
                       double* out, cudaStream_t st) {
   NQMC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)ctx->sys.P, st));
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_grads(ctx, r, wgt, hdr, e_l, W, out, st);
-  int rc = nq_launch_orb_bwd(ctx, r, wgt, hdr, e_l, W, out, st);
+  int rc = nq_launch_orb_bwd(ctx, ctx->sys.use_bf ? ctx->x_cur : r, wgt, hdr, e_l, W, out, st);
   if (rc) return rc;
-  return nq_launch_walker_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  rc = nq_launch_walker_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  if (rc) return rc;
+  if (ctx->sys.use_bf) rc = nq_launch_bf_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  return rc;
 }
 
 int nqmc_grad_accum(nqmc_ctx* ctx, const float* r, const float* weight, int64_t W, double* out, nqmc_stream st) {
@@ -367,7 +392,10 @@ int nqmc_grad_accum(nqmc_ctx* ctx, const float* r, const float* weight, int64_t 
   if (rc) return rc;
   if (!r || !out) return NQMC_ERR_ARG;
   NQMC_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC) {
+  if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC && ctx->sys.use_bf) {
+    rc = energy_core(ctx, r, W, nullptr, nullptr, S(st));      // fills x_cur, inv and v (needs orbital gradients)
+    if (rc) return rc;
+  } else if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC) {
     rc = nq_launch_orb_eval(ctx, r, W, 1, ctx->phi, S(st));
     if (rc) return rc;
     rc = nq_launch_assemble_inv(ctx, r, W, S(st));

@@ -58,16 +58,20 @@ struct nqmc_ctx {
   std::vector<LeafInfo> leaves;
   std::string err;
   int64_t launches = 0;
+  bool want_bf = false;        // backflow leaves exist in theta (use_backflow requested)
   // device state
   float* theta = nullptr;      // [P]
   int64_t cap_w = 0;           // reserved walkers
   float* r_prop = nullptr;     // [3N][cap_w]
-  float* phi = nullptr;        // [5][n_ent][cap_w]  orbital value / grad xyz / laplacian
+  float* phi = nullptr;        // [5 or 10][n_ent][cap_w]  orbital value / grad xyz / laplacian (or 6 Hessian entries)
   float* inv = nullptr;        // [n_ent][cap_w]     inverse orbital matrices (seeds of the reverse pass)
   float* logabs = nullptr;     // [cap_w]
   float* sign = nullptr;       // [cap_w]
   float* e_scratch = nullptr;  // [cap_w]
   float* wgt = nullptr;        // [cap_w]
+  float* x_cur = nullptr;      // [3N][cap_w] backflow coordinates of the current positions
+  float* x_prop = nullptr;     // [3N][cap_w] backflow coordinates of the proposal
+  float* vvec = nullptr;       // [3N][cap_w] v_i = sum_k inv[k,i] grad phi_k(x_i)  (backflow reverse pass)
   float* r_soa = nullptr;      // [3N][cap_w]  (host-entry staging)
   float* nrm_soa = nullptr;    // [3N][cap_w]
   float* aos_stage = nullptr;  // [cap_w][N][3]
@@ -191,3 +195,7 @@ int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
                      float* n_acc, cudaStream_t st);
 int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);
 int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st);
+int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cudaStream_t st);
+int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
+int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
+                       int64_t W, double* out, cudaStream_t st);

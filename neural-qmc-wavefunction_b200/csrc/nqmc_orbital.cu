@@ -43,7 +43,45 @@ __device__ __forceinline__ void act_rules(float (&v)[C]) {
     v[2] *= tp;
     v[3] *= tp;
   }
+  if constexpr (C == 10) {   // channels: value, d/dx d/dy d/dz, Hessian xx xy xz yy yz zz
+    float tp = fmaf(-h, h, 1.0f);
+    float tpp = -2.0f * h * tp;
+    v[4] = fmaf(tp, v[4], tpp * v[1] * v[1]);
+    v[5] = fmaf(tp, v[5], tpp * v[1] * v[2]);
+    v[6] = fmaf(tp, v[6], tpp * v[1] * v[3]);
+    v[7] = fmaf(tp, v[7], tpp * v[2] * v[2]);
+    v[8] = fmaf(tp, v[8], tpp * v[2] * v[3]);
+    v[9] = fmaf(tp, v[9], tpp * v[3] * v[3]);
+    v[1] *= tp;
+    v[2] *= tp;
+    v[3] *= tp;
+  }
   v[0] = h;
+}
+
+// RPT consecutive rows from shared memory (one 64/128-bit load per 2/4 rows)
+template <int RPT>
+__device__ __forceinline__ void load_rows(const float* p, float (&a)[RPT]) {
+  if constexpr (RPT == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    a[0] = t.x; a[1] = t.y;
+  } else {
+#pragma unroll
+    for (int v = 0; v < RPT / 4; ++v) {
+      float4 t = *reinterpret_cast<const float4*>(p + 4 * v);
+      a[4 * v] = t.x; a[4 * v + 1] = t.y; a[4 * v + 2] = t.z; a[4 * v + 3] = t.w;
+    }
+  }
+}
+template <int RPT>
+__device__ __forceinline__ void store_rows(float* p, const float (&a)[RPT]) {
+  if constexpr (RPT == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(a[0], a[1]);
+  } else {
+#pragma unroll
+    for (int v = 0; v < RPT / 4; ++v)
+      *reinterpret_cast<float4*>(p + 4 * v) = make_float4(a[4 * v], a[4 * v + 1], a[4 * v + 2], a[4 * v + 3]);
+  }
 }
 
 // orbital input features of one electron (phase2-issue-body.md:83-93) with their gradient / Laplacian
@@ -56,11 +94,12 @@ __device__ __forceinline__ void write_features(const DevSys& s, float x, float y
   for (int d = 0; d < 3; ++d) {
     float* f = Fs + d * SJ + row;
     f[0] = p[d];
-    if constexpr (C == 5) {
+    if constexpr (C >= 5) {
       f[1 * TR] = d == 0 ? 1.f : 0.f;
       f[2 * TR] = d == 1 ? 1.f : 0.f;
       f[3 * TR] = d == 2 ? 1.f : 0.f;
-      f[4 * TR] = 0.f;
+#pragma unroll
+      for (int c = 4; c < C; ++c) f[c * TR] = 0.f;
     }
   }
   for (int a = 0; a < s.A; ++a) {
@@ -83,6 +122,23 @@ __device__ __forceinline__ void write_features(const DevSys& s, float x, float y
       fe[2 * TR] = -e * uy;
       fe[3 * TR] = -e * uz;
       fe[4 * TR] = e * (1.0f - 2.0f * inv);
+    }
+    if constexpr (C == 10) {
+      // Hess d = (I - u u^T)/d ; Hess e^-d = e [u u^T (1 + 1/d) - I/d]
+      float inv = 1.0f / d;
+      float u[3] = {dx * inv, dy * inv, dz * inv};
+      fd[1 * TR] = u[0]; fd[2 * TR] = u[1]; fd[3 * TR] = u[2];
+      fe[1 * TR] = -e * u[0]; fe[2 * TR] = -e * u[1]; fe[3 * TR] = -e * u[2];
+      int c = 4;
+#pragma unroll
+      for (int a_ = 0; a_ < 3; ++a_)
+#pragma unroll
+        for (int b_ = a_; b_ < 3; ++b_) {
+          float uu = u[a_] * u[b_], dl = a_ == b_ ? 1.f : 0.f;
+          fd[c * TR] = (dl - uu) * inv;
+          fe[c * TR] = e * (uu * (1.0f + inv) - dl * inv);
+          ++c;
+        }
     }
   }
 }
@@ -163,11 +219,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           float a[RPT];
-#pragma unroll
-          for (int v = 0; v < RPT / 4; ++v) {
-            float4 t = *reinterpret_cast<const float4*>(As + f * SJ + c * TR + RPT * rg + 4 * v);
-            a[4 * v] = t.x; a[4 * v + 1] = t.y; a[4 * v + 2] = t.z; a[4 * v + 3] = t.w;
-          }
+          load_rows<RPT>(As + f * SJ + c * TR + RPT * rg, a);
 #pragma unroll
           for (int rr = 0; rr < RPT; ++rr) {
             acc[c][rr][0] = fmaf(a[rr], wv.x, acc[c][rr][0]);
@@ -192,11 +244,12 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
         for (int c = 0; c < C; ++c) acc[c][rr][jj] = v[c];
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c)
+      for (int c = 0; c < C; ++c) {
+        float o[RPT];
 #pragma unroll
-        for (int v = 0; v < RPT / 4; ++v)
-          *reinterpret_cast<float4*>(As + j * SJ + c * TR + RPT * rg + 4 * v) =
-              make_float4(acc[c][4 * v][jj], acc[c][4 * v + 1][jj], acc[c][4 * v + 2][jj], acc[c][4 * v + 3][jj]);
+        for (int rr = 0; rr < RPT; ++rr) o[rr] = acc[c][rr][jj];
+        store_rows<RPT>(As + j * SJ + c * TR + RPT * rg, o);
+      }
     }
     __syncthreads();
     // ---- layer 2 -------------------------------------------------------------------------
@@ -217,11 +270,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           float a[RPT];
-#pragma unroll
-          for (int v = 0; v < RPT / 4; ++v) {
-            float4 t = *reinterpret_cast<const float4*>(As + k * SJ + c * TR + RPT * rg + 4 * v);
-            a[4 * v] = t.x; a[4 * v + 1] = t.y; a[4 * v + 2] = t.z; a[4 * v + 3] = t.w;
-          }
+          load_rows<RPT>(As + k * SJ + c * TR + RPT * rg, a);
 #pragma unroll
           for (int rr = 0; rr < RPT; ++rr) {
             acc[c][rr][0] = fmaf(a[rr], wv.x, acc[c][rr][0]);
@@ -628,7 +677,7 @@ int launch_eval_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStre
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
   {
-    ProfScope ps(ctx, C == 5 ? NQ_PROF_EVAL5 : NQ_PROF_EVAL1, st);
+    ProfScope ps(ctx, C >= 5 ? NQ_PROF_EVAL5 : NQ_PROF_EVAL1, st);
     kern<<<n_chunks * s.n_mlp, NT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
   }
   NQMC_LAUNCH_CHECK();
@@ -685,6 +734,11 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
     if (H == 32) return launch_eval_t<32, 5, 4, 256>(ctx, r, W, phi, st);
     if (H == 64) return launch_eval_t<64, 5, 4, 256>(ctx, r, W, phi, st);
     if (H == 128) return launch_eval_t<128, 5, 4, 256>(ctx, r, W, phi, st);
+  }
+  else if (channels == 10) {
+    if (H == 32) return launch_eval_t<32, 10, 2, 256>(ctx, r, W, phi, st);
+    if (H == 64) return launch_eval_t<64, 10, 2, 256>(ctx, r, W, phi, st);
+    if (H == 128) return launch_eval_t<128, 10, 2, 256>(ctx, r, W, phi, st);
   }
   ctx->err = "orb_eval: unsupported hidden width / channel count";
   return NQMC_ERR_UNSUPPORTED;

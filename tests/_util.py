@@ -3,17 +3,22 @@ import numpy as np
 
 from oracle.layout import KIND_ANTISYMMETRIC, KIND_SIMPLE, OracleNet, OracleSystem, hydrogen_chain_system, init_theta, param_count
 from oracle.nqmc_oracle import Oracle
+from oracle.nqmc_backflow import BackflowOracle
+
+
+def make_oracle(s, net):
+    return BackflowOracle(s, net) if net.use_backflow else Oracle(s, net)
 
 
 def make_case(n_atoms=4, hidden=64, kind=KIND_ANTISYMMETRIC, use_cusp=False, W=512, seed=0, bond=1.8, burn=30,
-              sigma=0.3):
+              sigma=0.3, use_backflow=False):
     """-> (sys, net, theta(float32), r(float32, (W,N,3)) roughly |psi|^2-distributed)."""
     s = hydrogen_chain_system(n_atoms, bond)
-    net = OracleNet(kind=kind, hidden=(hidden, hidden), use_cusp=use_cusp)
+    net = OracleNet(kind=kind, hidden=(hidden, hidden), use_cusp=use_cusp, use_backflow=use_backflow)
     theta = init_theta(s, net, seed + 1).astype(np.float32)
     rng = np.random.default_rng(seed)
     r = s.R[np.arange(s.n_elec) % s.n_atoms][None] + 0.5 * rng.standard_normal((W, s.n_elec, 3))   # vmc.py:199-208
-    o = Oracle(s, net)
+    o = make_oracle(s, net)
     th64 = theta.astype(np.float64)
     _, la = o.log_psi(th64, r)
     logp = 2 * la

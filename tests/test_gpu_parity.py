@@ -13,7 +13,7 @@ from oracle.layout import KIND_ANTISYMMETRIC, KIND_SIMPLE
 from oracle.nqmc_oracle import Oracle
 from oracle import philox
 
-from _util import make_case, make_context, rel_err
+from _util import make_case, make_context, make_oracle, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -25,10 +25,13 @@ CASES = [
     dict(n_atoms=6, hidden=64, W=384, use_cusp=True),
     dict(n_atoms=6, hidden=128, W=200, use_cusp=True),
     dict(n_atoms=10, hidden=128, W=96),
+    dict(n_atoms=2, hidden=32, W=200, use_backflow=True),
+    dict(n_atoms=4, hidden=64, W=300, use_backflow=True),
+    dict(n_atoms=6, hidden=128, W=160, use_cusp=True, use_backflow=True),
     dict(n_atoms=2, hidden=64, W=200, kind=KIND_SIMPLE),
     dict(n_atoms=4, hidden=48, W=130, kind=KIND_SIMPLE),
 ]
-IDS = [f"H{c['n_atoms']}-h{c['hidden']}-W{c['W']}" + ("-cusp" if c.get("use_cusp") else "") + ("-simple" if c.get("kind") == KIND_SIMPLE else "") for c in CASES]
+IDS = [f"H{c['n_atoms']}-h{c['hidden']}-W{c['W']}" + ("-cusp" if c.get("use_cusp") else "") + ("-bf" if c.get("use_backflow") else "") + ("-simple" if c.get("kind") == KIND_SIMPLE else "") for c in CASES]
 
 
 def q(x):
@@ -41,7 +44,7 @@ def case(request):
     s, net, theta, r = make_case(**request.param)
     ctx = make_context(s, net)
     ctx.set_params(theta)
-    return dict(s=s, net=net, theta=theta, r=r, ctx=ctx, oracle=Oracle(s, net), th64=theta.astype(np.float64),
+    return dict(s=s, net=net, theta=theta, r=r, ctx=ctx, oracle=make_oracle(s, net), th64=theta.astype(np.float64),
                 r64=r.astype(np.float64), soa=ctx.to_soa(r))
 
 

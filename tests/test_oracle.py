@@ -176,3 +176,19 @@ def test_estimator_identities():
     swp = rb.copy(); swp[:, [0, 1]] = swp[:, [1, 0]]
     s1, l1 = a.log_psi(thb, rb); s2, l2 = a.log_psi(thb, swp)
     assert np.allclose(l1, l2, rtol=1e-8) and np.array_equal(s1, -s2)     # backflow keeps antisymmetry
+
+
+@pytest.mark.parametrize("n_atoms,cusp", [(2, False), (4, False), (6, True)])
+def test_backflow_analytic_equals_autodiff_fp64(n_atoms, cusp):
+    """K-8 for the backflow ansatz: orbital-Hessian chain rule (Appendix C.3) == nested autodiff."""
+    from oracle.nqmc_backflow import BackflowOracle
+    s, net, th, r = _case(n_atoms, cusp=cusp, bf=True, W=6)
+    o, a = BackflowOracle(s, net), AutodiffOracle(s, net)
+    sg, la = o.log_psi(th, r)
+    sg2, la2 = a.log_psi(th, r)
+    assert np.array_equal(sg, sg2) and np.max(np.abs(la - la2)) < 1e-10
+    e, _, _, _ = o.local_energy(th, r)
+    e2 = a.local_energy(th, r)
+    assert np.max(np.abs(e - e2) / np.maximum(1, np.abs(e2))) < 1e-9
+    O, O2 = o.grad_log_psi(th, r), a.grad_log_psi(th, r)
+    assert np.max(np.abs(O - O2) / np.maximum(1, np.abs(O2))) < 1e-9
