@@ -1,0 +1,85 @@
+"""Independent walker sets over several geometries (BASELINE config 4: the H4 dissociation sweep,
+R = linspace(1.0, 4.0, 16), `.github/phase4-issue-body.md:168-200` scan_pes).
+
+The reference trains one geometry after another in a Python loop.  Geometries share nothing -- each has
+its own nuclei, V_nn, parameters theta and walkers -- so they are independent units: no collective, and
+across GPUs geometry g simply runs on rank g % world.  Here every geometry owns a device context; one
+`step()` advances all local geometries by one fused walker step (MH move, E_L, weighted gradient sums),
+back to back on the current stream (each launch already fills the 148 SMs at >= 16k walkers).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import parallel
+from . import random as nqrandom
+from .params import ravel
+from .systems.molecule import hydrogen_chain
+from .wavefunction import AntisymmetricWavefunction
+
+
+@dataclass
+class GeometryState:
+    bond_length: float
+    molecule: object
+    wavefunction: object
+    params: dict
+    ctx: object
+    r: object            # device SoA [3N, W]
+    logp: object         # device [W]
+    e_l: object
+    hdr: object
+    gsum: object
+
+
+class GeometrySweep:
+    def __init__(self, bond_lengths: Sequence[float] = tuple(np.linspace(1.0, 4.0, 16)), n_atoms: int = 4,
+                 walkers_per_geometry: int = 16384, hidden=(64, 64), use_cusp: bool = False, use_backflow: bool = False,
+                 step_size: float = 0.5, seed: int = 42):
+        import torch
+        self.step_size, self.seed, self.W = float(step_size), int(seed), int(walkers_per_geometry)
+        rank, ws = parallel.world()
+        self.local_ids = [g for g in range(len(bond_lengths)) if g % ws == rank]
+        self.states: List[GeometryState] = []
+        for g in self.local_ids:
+            R = float(bond_lengths[g])
+            mol = hydrogen_chain(n_atoms, R)
+            wf = AntisymmetricWavefunction(n_atoms // 2, n_atoms // 2, hidden, use_cusp=use_cusp, use_backflow=use_backflow,
+                                           molecule=mol)
+            params = wf.init(nqrandom.PRNGKey(seed + g))
+            ctx = wf.context(mol)
+            ctx.set_params(ravel(params))
+            rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, g, 0]))
+            pos = np.asarray(mol.positions, np.float32)[np.arange(mol.n_electrons) % mol.n_atoms][None]
+            r0 = (pos + 0.5 * rng.standard_normal((self.W, mol.n_electrons, 3))).astype(np.float32)
+            r = ctx.to_soa(r0)
+            _, la = ctx.log_psi(r)
+            dev = ctx.dev()
+            self.states.append(GeometryState(R, mol, wf, params, ctx, r, (2.0 * la).contiguous(),
+                                             torch.empty(self.W, dtype=torch.float32, device=dev),
+                                             torch.empty(8, dtype=torch.float64, device=dev),
+                                             torch.empty(ctx.P, dtype=torch.float64, device=dev)))
+        self.t = 0
+
+    def burn_in(self, n_steps: int):
+        for st, g in zip(self.states, self.local_ids):
+            for t in range(n_steps):
+                st.ctx.mh_step(st.r, st.logp, self.step_size, seed=self.seed + 1000 * g, step=t)
+
+    def step(self):
+        """One fused walker step for every local geometry; returns [(bond, mean E, stderr, grad)] lazily as device data."""
+        self.t += 1
+        for st, g in zip(self.states, self.local_ids):
+            st.ctx.walker_step(st.r, st.logp, self.step_size, st.e_l, st.hdr, st.gsum, seed=self.seed + 1000 * g,
+                               step=(1 << 20) + self.t)
+
+    def results(self):
+        out = []
+        for st in self.states:
+            grad, mean, std = parallel.combine_gradient(st.hdr.cpu().numpy(), st.gsum.cpu().numpy())
+            out.append({"bond_length": st.bond_length, "energy": mean, "std": std, "gradient": grad,
+                        "v_nn": st.molecule.nuclear_repulsion_energy()})
+        return out
