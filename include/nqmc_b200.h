@@ -169,6 +169,9 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, co
 /* ---- introspection --------------------------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t nqmc_launch_count(const nqmc_ctx* ctx);
+/* Select the tcgen05 / TMEM 3xTF32 variant of the hidden-layer GEMMs where one exists (default on; the
+ * environment variable NQMC_TC=0 turns it off at create time).  The FP32 FFMA kernels are the parity anchor. */
+int nqmc_use_tensor_cores(nqmc_ctx* ctx, int enable);
 /* Per-kernel CUDA-event timing on the launching stream (used by bench.py for the roofline leg).
  * kind: 0 orbital forward (value), 1 orbital forward (value+grad+Laplacian), 2 orbital reverse pass,
  *       3 Slater/Jastrow/E_L assembly, 4 accept.  nqmc_profile(ctx, 1) resets and enables; _read

@@ -1,6 +1,7 @@
 // nqmc_api.cu -- the C ABI of include/nqmc_b200.h: context, parameter map, entry points.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "nqmc_internal.cuh"
@@ -188,6 +189,7 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
     for (int d = 0; d < 3; ++d) s.R[3 * a + d] = (float)sys->R[3 * a + d];
     s.Z[a] = (float)sys->Z[a];
   }
+  if (const char* e = getenv("NQMC_TC")) ctx->use_tc = atoi(e) != 0;
   ctx->want_bf = net->kind == NQMC_KIND_ANTISYMMETRIC && net->use_backflow != 0;
   build_param_map(ctx);
   ctx->p_mlp = s.kind == NQMC_KIND_ANTISYMMETRIC ? (s.F * s.H + s.H + s.H * s.H + s.H + s.H + 1) : s.P;
@@ -483,6 +485,12 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
 }
 
 int64_t nqmc_launch_count(const nqmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int nqmc_use_tensor_cores(nqmc_ctx* ctx, int enable) {
+  if (!ctx) return NQMC_ERR_ARG;
+  ctx->use_tc = enable != 0;
+  return NQMC_OK;
+}
 
 int nqmc_profile(nqmc_ctx* ctx, int enable) {
   if (!ctx) return NQMC_ERR_ARG;

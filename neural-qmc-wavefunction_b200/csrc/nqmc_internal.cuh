@@ -58,6 +58,7 @@ struct nqmc_ctx {
   std::vector<LeafInfo> leaves;
   std::string err;
   int64_t launches = 0;
+  bool use_tc = true;          // tcgen05 3xTF32 path for the H x H layers where a variant exists (NQMC_TC=0 disables)
   bool want_bf = false;        // backflow leaves exist in theta (use_backflow requested)
   // device state
   float* theta = nullptr;      // [P]
@@ -199,3 +200,4 @@ int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cud
 int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
 int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                        int64_t W, double* out, cudaStream_t st);
+int nq_launch_orb_eval5_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);

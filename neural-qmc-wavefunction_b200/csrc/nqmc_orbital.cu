@@ -59,6 +59,32 @@ __device__ __forceinline__ void act_rules(float (&v)[C]) {
   v[0] = h;
 }
 
+// Packed FP32 FMA (Blackwell FFMA2): two rows per instruction.  ptxas folds the duplicated weight
+// into a broadcast operand (FFMA2 Rd, Ra.F32x2.HI_LO, Rw.F32, Rd.F32x2.HI_LO), so the FMA pipe sees
+// the same work in half the issue slots -- the orbital GEMM loops are issue-bound otherwise.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// acc[rp][jj] (rows 2rp, 2rp+1 ; column jj) += a[rows] * w[jj]
+template <int RPT>
+__device__ __forceinline__ void fma_tile(float2 (&acc)[RPT / 2][4], const float (&a)[RPT], const float4& wv) {
+#pragma unroll
+  for (int rp = 0; rp < RPT / 2; ++rp) {
+    const float2 ap = make_float2(a[2 * rp], a[2 * rp + 1]);
+    acc[rp][0] = ffma2(ap, make_float2(wv.x, wv.x), acc[rp][0]);
+    acc[rp][1] = ffma2(ap, make_float2(wv.y, wv.y), acc[rp][1]);
+    acc[rp][2] = ffma2(ap, make_float2(wv.z, wv.z), acc[rp][2]);
+    acc[rp][3] = ffma2(ap, make_float2(wv.w, wv.w), acc[rp][3]);
+  }
+}
+
 // RPT consecutive rows from shared memory (one 64/128-bit load per 2/4 rows)
 template <int RPT>
 __device__ __forceinline__ void load_rows(const float* p, float (&a)[RPT]) {
@@ -201,18 +227,19 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
     }
     __syncthreads();
 
-    float acc[C][RPT][4];
+    float2 acc[C][RPT / 2][4];
+#define ACC(c, rr, jj) ((rr) & 1 ? acc[c][(rr) >> 1][jj].y : acc[c][(rr) >> 1][jj].x)
     // ---- layer 1 -------------------------------------------------------------------------
     {
       const float4 bv = *reinterpret_cast<const float4*>(b1p + 4 * cg);
 #pragma unroll
       for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int rr = 0; rr < RPT; ++rr) {
-          acc[c][rr][0] = c == 0 ? bv.x : 0.f;
-          acc[c][rr][1] = c == 0 ? bv.y : 0.f;
-          acc[c][rr][2] = c == 0 ? bv.z : 0.f;
-          acc[c][rr][3] = c == 0 ? bv.w : 0.f;
+        for (int rp = 0; rp < RPT / 2; ++rp) {
+          acc[c][rp][0] = c == 0 ? make_float2(bv.x, bv.x) : make_float2(0.f, 0.f);
+          acc[c][rp][1] = c == 0 ? make_float2(bv.y, bv.y) : make_float2(0.f, 0.f);
+          acc[c][rp][2] = c == 0 ? make_float2(bv.z, bv.z) : make_float2(0.f, 0.f);
+          acc[c][rp][3] = c == 0 ? make_float2(bv.w, bv.w) : make_float2(0.f, 0.f);
         }
       for (int f = 0; f < F; ++f) {
         const float4 wv = *reinterpret_cast<const float4*>(W1p + f * H + 4 * cg);
@@ -220,13 +247,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
         for (int c = 0; c < C; ++c) {
           float a[RPT];
           load_rows<RPT>(As + f * SJ + c * TR + RPT * rg, a);
-#pragma unroll
-          for (int rr = 0; rr < RPT; ++rr) {
-            acc[c][rr][0] = fmaf(a[rr], wv.x, acc[c][rr][0]);
-            acc[c][rr][1] = fmaf(a[rr], wv.y, acc[c][rr][1]);
-            acc[c][rr][2] = fmaf(a[rr], wv.z, acc[c][rr][2]);
-            acc[c][rr][3] = fmaf(a[rr], wv.w, acc[c][rr][3]);
-          }
+          fma_tile<RPT>(acc[c], a, wv);
         }
       }
     }
@@ -238,16 +259,19 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
       for (int rr = 0; rr < RPT; ++rr) {
         float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = acc[c][rr][jj];
+        for (int c = 0; c < C; ++c) v[c] = ACC(c, rr, jj);
         act_rules<C>(v);
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c][rr][jj] = v[c];
+        for (int c = 0; c < C; ++c) {
+          if (rr & 1) acc[c][rr >> 1][jj].y = v[c];
+          else acc[c][rr >> 1][jj].x = v[c];
+        }
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float o[RPT];
 #pragma unroll
-        for (int rr = 0; rr < RPT; ++rr) o[rr] = acc[c][rr][jj];
+        for (int rr = 0; rr < RPT; ++rr) o[rr] = ACC(c, rr, jj);
         store_rows<RPT>(As + j * SJ + c * TR + RPT * rg, o);
       }
     }
@@ -258,11 +282,11 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
 #pragma unroll
       for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int rr = 0; rr < RPT; ++rr) {
-          acc[c][rr][0] = c == 0 ? bv.x : 0.f;
-          acc[c][rr][1] = c == 0 ? bv.y : 0.f;
-          acc[c][rr][2] = c == 0 ? bv.z : 0.f;
-          acc[c][rr][3] = c == 0 ? bv.w : 0.f;
+        for (int rp = 0; rp < RPT / 2; ++rp) {
+          acc[c][rp][0] = c == 0 ? make_float2(bv.x, bv.x) : make_float2(0.f, 0.f);
+          acc[c][rp][1] = c == 0 ? make_float2(bv.y, bv.y) : make_float2(0.f, 0.f);
+          acc[c][rp][2] = c == 0 ? make_float2(bv.z, bv.z) : make_float2(0.f, 0.f);
+          acc[c][rp][3] = c == 0 ? make_float2(bv.w, bv.w) : make_float2(0.f, 0.f);
         }
 #pragma unroll 2
       for (int k = 0; k < H; ++k) {
@@ -271,13 +295,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
         for (int c = 0; c < C; ++c) {
           float a[RPT];
           load_rows<RPT>(As + k * SJ + c * TR + RPT * rg, a);
-#pragma unroll
-          for (int rr = 0; rr < RPT; ++rr) {
-            acc[c][rr][0] = fmaf(a[rr], wv.x, acc[c][rr][0]);
-            acc[c][rr][1] = fmaf(a[rr], wv.y, acc[c][rr][1]);
-            acc[c][rr][2] = fmaf(a[rr], wv.z, acc[c][rr][2]);
-            acc[c][rr][3] = fmaf(a[rr], wv.w, acc[c][rr][3]);
-          }
+          fma_tile<RPT>(acc[c], a, wv);
         }
       }
     }
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
         for (int rr = 0; rr < RPT; ++rr) {
           float v[C];
 #pragma unroll
-          for (int c = 0; c < C; ++c) v[c] = acc[c][rr][jj];
+          for (int c = 0; c < C; ++c) v[c] = ACC(c, rr, jj);
           act_rules<C>(v);
 #pragma unroll
           for (int c = 0; c < C; ++c) out[c][rr] = fmaf(w3a[jj], v[c], out[c][rr]);
@@ -322,6 +340,7 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
     }
     __syncthreads();   // next tile's features overwrite A
   }
+#undef ACC
 }
 
 // ============================================================================================
@@ -731,6 +750,10 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
     if (H == 64) return launch_eval_t<64, 1, 8, 256>(ctx, r, W, phi, st);
     if (H == 128) return launch_eval_t<128, 1, 8, 256>(ctx, r, W, phi, st);
   } else if (channels == 5) {
+    if (ctx->use_tc) {
+      int rc = nq_launch_orb_eval5_tc(ctx, r, W, phi, st);
+      if (rc != NQMC_ERR_UNSUPPORTED) return rc;
+    }
     if (H == 32) return launch_eval_t<32, 5, 4, 256>(ctx, r, W, phi, st);
     if (H == 64) return launch_eval_t<64, 5, 4, 256>(ctx, r, W, phi, st);
     if (H == 128) return launch_eval_t<128, 5, 4, 256>(ctx, r, W, phi, st);

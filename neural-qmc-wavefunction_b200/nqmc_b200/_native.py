@@ -25,7 +25,7 @@ EXPORTS = [
     "nqmc_leaf_info", "nqmc_set_params", "nqmc_set_params_host", "nqmc_aos_to_soa", "nqmc_soa_to_aos",
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
-    "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak",
+    "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     lib.nqmc_launch_count.restype = i64
     lib.nqmc_rng_fill.argtypes = [vp, u64, u64, i64, i64, vp, vp, vp]
     lib.nqmc_profile.argtypes = [vp, C.c_int]
+    lib.nqmc_use_tensor_cores.argtypes = [vp, C.c_int]
     lib.nqmc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.nqmc_ffma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp]
     _lib = lib
@@ -280,6 +281,9 @@ class Context:
                                                    np_ptr(uniforms), int(seed) & (2**64 - 1), int(step), int(walker_id0),
                                                    float(sigma), W, e_l.ctypes.data, hdr.ctypes.data, gsum.ctypes.data,
                                                    self.stream), "nqmc_walker_step_host")
+
+    def use_tensor_cores(self, enable: bool):
+        self._check(self.lib.nqmc_use_tensor_cores(self.h, int(enable)), "nqmc_use_tensor_cores")
 
     def profile(self, enable: bool):
         self._check(self.lib.nqmc_profile(self.h, int(enable)), "nqmc_profile")
