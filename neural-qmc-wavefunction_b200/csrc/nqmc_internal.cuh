@@ -201,3 +201,5 @@ int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, 
 int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                        int64_t W, double* out, cudaStream_t st);
 int nq_launch_orb_eval5_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
+int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
+                         int* n_chunks_out, cudaStream_t st);

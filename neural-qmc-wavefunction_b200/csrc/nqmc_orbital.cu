@@ -770,6 +770,17 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
 int nq_launch_orb_bwd(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                       int64_t W, double* out, cudaStream_t st) {
   const int H = ctx->sys.H;
+  if (ctx->use_tc) {
+    int nc = 0;
+    int rc = nq_launch_orb_bwd_tc(ctx, r, wgt, hdr_center, e_l, W, &nc, st);
+    if (rc == NQMC_OK) {
+      dim3 g((ctx->p_mlp + 255) / 256, ctx->sys.n_mlp);
+      orb_bwd_reduce_kernel<<<g, 256, 0, st>>>(ctx->sys, ctx->part_mlp, nc, ctx->p_mlp, out);
+      NQMC_LAUNCH_CHECK();
+      return NQMC_OK;
+    }
+    if (rc != NQMC_ERR_UNSUPPORTED) return rc;
+  }
   if (H == 32) return launch_bwd_t<32, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);
   if (H == 64) return launch_bwd_t<64, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);
   if (H == 128) return launch_bwd_t<128, 256>(ctx, r, wgt, hdr_center, e_l, W, out, st);

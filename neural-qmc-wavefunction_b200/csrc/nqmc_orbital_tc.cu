@@ -24,10 +24,13 @@
 namespace {
 
 constexpr int H = 64;
-constexpr int TCW = 256;            // worker threads (8 warps): layer 1, operand staging, epilogue
+constexpr int NQ = 4;                // threads per row (each owns 64/NQ output columns and 32/NQ layer-1 units per pass)
+constexpr int TCW = 128 * NQ;        // worker threads: layer 1, operand staging, epilogue
 constexpr int TCT = TCW + 32;       // + one warp whose lane 0 issues the UMMAs
 constexpr int ROWS = 128;           // rows per tile == UMMA M
 constexpr int KC = 16;              // hidden units per K-chunk
+constexpr int UPT = 32 / NQ;        // layer-1 hidden units per thread per pass
+constexpr int EPC = H / NQ;         // epilogue columns per thread
 constexpr int CH = 5;               // value, d/dx, d/dy, d/dz, Laplacian
 constexpr uint32_t TMEM_COLS = 512;
 // operand buffers (bytes)
@@ -36,7 +39,7 @@ constexpr int A_CHUNK = (KC / 4) * A_K4;        // one (channel, hi|lo) K-chunk 
 constexpr int A_BUF = CH * 2 * A_CHUNK;         // one K-chunk, all channels, hi+lo           = 81920
 constexpr int B_K4 = H * 16;                    // one k/4 group of W2^T: 64 n x 16 B         = 1024
 constexpr int B_MAT = (H / 4) * B_K4;           // W2 hi (or lo)                              = 16384
-constexpr int SMEM_BYTES = 2 * A_BUF + 2 * B_MAT + (35 * H + 3 * H) * 4 + ROWS * CH * 4 + 64;
+constexpr int SMEM_BYTES = 2 * A_BUF + 2 * B_MAT + (35 * H + 3 * H) * 4 + (NQ - 1) * ROWS * CH * 4 + 64;
 
 // UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -48,15 +51,24 @@ constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// issued from warp-uniform code by the whole issuer warp; only the elected lane (leader != 0) executes the MMA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
+                                          uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      "{\n\t.reg .pred p, l;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 l, %5, 0;\n\t"
+      "@l tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(leader)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+  asm volatile("{\n\t.reg .pred l;\n\tsetp.ne.b32 l, %1, 0;\n\t"
+               "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+               : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -80,9 +92,122 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
   lo = a - hi;
+}
+
+// layer 1 (FP32 FFMA) for hidden units j0 .. j0+15 of one row, 5 channels, followed by the tanh rules
+__device__ __forceinline__ void layer1_pass(const DevSys& s, const float* __restrict__ W1s, const float* __restrict__ b1s,
+                                            const float x, const float y, const float z, const int j0,
+                                            float (&acc)[CH][UPT]) {
+  const int A = s.A;
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) {
+    acc[0][j] = b1s[j0 + j];
+#pragma unroll
+    for (int c = 1; c < CH; ++c) acc[c][j] = 0.f;
+  }
+  {  // coordinate features: value p_d, gradient e_d, Laplacian 0
+    const float pc[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int v = 0; v < UPT / 4; ++v) {
+        const float4 wv = *reinterpret_cast<const float4*>(W1s + d * H + j0 + 4 * v);
+        const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc[0][4 * v + t] = fmaf(pc[d], wa[t], acc[0][4 * v + t]);
+          acc[1 + d][4 * v + t] += wa[t];
+        }
+      }
+    }
+  }
+  for (int a = 0; a < A; ++a) {
+    const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+    const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    const float ex = __expf(-dd), inv = 1.0f / dd;
+    const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+    const float fd[CH] = {dd, ux, uy, uz, 2.0f * inv};
+    const float fe[CH] = {ex, -ex * ux, -ex * uy, -ex * uz, ex * (1.0f - 2.0f * inv)};
+#pragma unroll
+    for (int v = 0; v < UPT / 4; ++v) {
+      const float4 wd = *reinterpret_cast<const float4*>(W1s + (3 + a) * H + j0 + 4 * v);
+      const float4 we = *reinterpret_cast<const float4*>(W1s + (3 + A + a) * H + j0 + 4 * v);
+      const float wda[4] = {wd.x, wd.y, wd.z, wd.w}, wea[4] = {we.x, we.y, we.z, we.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c][4 * v + t] = fmaf(fd[c], wda[t], fmaf(fe[c], wea[t], acc[c][4 * v + t]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) {   // tanh rules, thread-local across the 5 channels
+    const float h = nq_tanh(acc[0][j]);
+    const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
+    const float g2 = fmaf(acc[1][j], acc[1][j], fmaf(acc[2][j], acc[2][j], acc[3][j] * acc[3][j]));
+    acc[4][j] = fmaf(tp, acc[4][j], tpp * g2);
+    acc[1][j] *= tp; acc[2][j] *= tp; acc[3][j] *= tp;
+    acc[0][j] = h;
+  }
+}
+
+// hi/lo split and store as UMMA K-major core matrices [k/4][row][k%4]; then make the writes visible to the async proxy
+__device__ __forceinline__ void store_operand(uint8_t* buf, const float (&acc)[CH][UPT]) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int v = 0; v < UPT / 4; ++v) {
+      float4 hi4, lo4;
+      split_tf32(acc[c][4 * v + 0], hi4.x, lo4.x);
+      split_tf32(acc[c][4 * v + 1], hi4.y, lo4.y);
+      split_tf32(acc[c][4 * v + 2], hi4.z, lo4.z);
+      split_tf32(acc[c][4 * v + 3], hi4.w, lo4.w);
+      *reinterpret_cast<float4*>(buf + (c * 2 + 0) * A_CHUNK + v * A_K4) = hi4;
+      *reinterpret_cast<float4*>(buf + (c * 2 + 1) * A_CHUNK + v * A_K4) = lo4;
+    }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// one thread: 5 channels x 2 K-chunks x 2 k-steps x 3 products, then commit to `bar`
+template <int p>
+__device__ __forceinline__ void issue_pass( const uint32_t tmem_base, const uint32_t a_base,
+                                           const uint32_t bhi_base, const uint32_t blo_base, const uint32_t bar) {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t leader = elect_one();
+  // descriptors differ only in their 14-bit start-address field: precompute the bases once
+  const uint64_t dA = umma_desc(a_base, A_K4, 128), dBh = umma_desc(bhi_base, B_K4, 128), dBl = umma_desc(blo_base, B_K4, 128);
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int kchunk = 2 * hh + p;                       // hidden units 32*hh + 16*p ..
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)(c * H);
+#pragma unroll
+      for (int ks = 0; ks < KC / 8; ++ks) {
+        const uint64_t dah = dA + (uint64_t)((hh * A_BUF + (c * 2 + 0) * A_CHUNK + ks * 2 * A_K4) >> 4);
+        const uint64_t dal = dA + (uint64_t)((hh * A_BUF + (c * 2 + 1) * A_CHUNK + ks * 2 * A_K4) >> 4);
+        const uint64_t kb = (uint64_t)(((kchunk * (KC / 4) + ks * 2) * B_K4) >> 4);
+        const uint64_t dbh = dBh + kb, dbl = dBl + kb;
+        const uint32_t first = (p == 0 && hh == 0 && ks == 0) ? 0u : 1u;
+        umma_tf32(d_tmem, dah, dbh, first, leader);
+        umma_tf32(d_tmem, dal, dbh, 1u, leader);
+        umma_tf32(d_tmem, dah, dbl, 1u, leader);
+      }
+    }
+  }
+  umma_commit(bar, leader);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(TCT, 1)
@@ -96,22 +221,24 @@ __global__ void __launch_bounds__(TCT, 1)
   float* b1s = W1s + 35 * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
-  float* outS = W3s + H;                                      // [ROWS][CH] partial outputs of half 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(outS + ROWS * CH);   // 2 mbarriers
+  float* outS = W3s + H;                                      // [NQ-1][ROWS][CH] partial outputs of quarters 1..
+  uint64_t* bars = reinterpret_cast<uint64_t*>(outS + (NQ - 1) * ROWS * CH);   // 2 mbarriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & (ROWS - 1), half = (tid >> 7) & 1;
+  const int row = tid & (ROWS - 1), quarter = (tid >> 7) & (NQ - 1);
+  // layer-1 ownership: K-chunk buffer hh = quarter / (NQ/2), units 16*p + UPT*(quarter % (NQ/2)) inside it
+  const int hh_own = quarter / (NQ / 2), sub_own = quarter % (NQ / 2);
+  const bool worker = tid < TCW;
   const int m = blockIdx.x % s.n_mlp, chunk = blockIdx.x / s.n_mlp;
   const int spin = m < s.n_up ? 0 : 1;
   const int korb = spin == 0 ? m : m - s.n_up;
   const int ns = spin == 0 ? s.n_up : s.n_dn;
   const int elec0 = spin == 0 ? 0 : s.n_up;
   const MlpOff off = s.mlp[m];
-  const int F = s.F, A = s.A;
+  const int F = s.F;
 
   // ---- one-time setup: weights, barriers, tensor memory -----------------------------------------
-  const bool worker = tid < TCW;
   for (int idx = tid; idx < F * H; idx += TCT) W1s[idx] = theta[off.W1 + idx];
   for (int q = tid; q < H; q += TCT) {
     b1s[q] = theta[off.b1 + q];
@@ -146,166 +273,100 @@ __global__ void __launch_bounds__(TCT, 1)
   const uint32_t a_base = smem_u32(Abuf), bhi_base = smem_u32(Bhi), blo_base = smem_u32(Blo);
   const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
   uint32_t phase0 = 0, phase1 = 0;
+  uint8_t* my_buf = Abuf + hh_own * A_BUF + sub_own * (UPT / 4) * A_K4 + row * 16;
+  const int j_own = 32 * hh_own + UPT * sub_own;             // + KC * pass
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
+  // position of this thread's row in tile `it`
+  auto load_xyz = [&](int64_t it, float& x, float& y, float& z) {
+    int64_t w = (it / ns) * ROWS + row;
+    if (w >= W) w = W - 1;
+    const int e = elec0 + (int)(it % ns);
+    x = r[(int64_t)(3 * e + 0) * W + w];
+    y = r[(int64_t)(3 * e + 1) * W + w];
+    z = r[(int64_t)(3 * e + 2) * W + w];
+  };
+
+  // software pipeline: pass 0 of tile t+1 is computed while the tensor cores finish tile t
+  float acc[CH][UPT];
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (worker && chunk < n_items) {
+    load_xyz(chunk, x, y, z);
+    layer1_pass(s, W1s, b1s, x, y, z, j_own, acc);
+  }
   for (int64_t item = chunk; item < n_items; item += n_chunks) {
     const int i = (int)(item % ns);
     const int64_t w0 = (item / ns) * ROWS;
-    int64_t w = w0 + row;
-    if (w >= W) w = W - 1;
-    const int e = elec0 + i;
-    const float x = r[(int64_t)(3 * e + 0) * W + w], y = r[(int64_t)(3 * e + 1) * W + w], z = r[(int64_t)(3 * e + 2) * W + w];
-
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-     if (worker) {
-      // ---- layer 1 for hidden units j0 .. j0+15, this row, 5 channels ------------------------------
-      const int j0 = 32 * half + KC * p;
-      float acc[CH][KC];
-#pragma unroll
-      for (int j = 0; j < KC; ++j) {
-        acc[0][j] = b1s[j0 + j];
-#pragma unroll
-        for (int c = 1; c < CH; ++c) acc[c][j] = 0.f;
-      }
-      // coordinate features: value p_d, gradient e_d, Laplacian 0
-      {
-        const float pc[3] = {x, y, z};
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-#pragma unroll
-          for (int v = 0; v < KC / 4; ++v) {
-            const float4 wv = *reinterpret_cast<const float4*>(W1s + d * H + j0 + 4 * v);
-            const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              acc[0][4 * v + t] = fmaf(pc[d], wa[t], acc[0][4 * v + t]);
-              acc[1 + d][4 * v + t] += wa[t];
-            }
-          }
-        }
-      }
-      for (int a = 0; a < A; ++a) {
-        const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
-        const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        const float ex = __expf(-dd), inv = 1.0f / dd;
-        const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
-        const float fd[CH] = {dd, ux, uy, uz, 2.0f * inv};
-        const float fe[CH] = {ex, -ex * ux, -ex * uy, -ex * uz, ex * (1.0f - 2.0f * inv)};
-#pragma unroll
-        for (int v = 0; v < KC / 4; ++v) {
-          const float4 wd = *reinterpret_cast<const float4*>(W1s + (3 + a) * H + j0 + 4 * v);
-          const float4 we = *reinterpret_cast<const float4*>(W1s + (3 + A + a) * H + j0 + 4 * v);
-          const float wda[4] = {wd.x, wd.y, wd.z, wd.w}, wea[4] = {we.x, we.y, we.z, we.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c][4 * v + t] = fmaf(fd[c], wda[t], fmaf(fe[c], wea[t], acc[c][4 * v + t]));
-        }
-      }
-      // tanh rules, thread-local across the 5 channels
-#pragma unroll
-      for (int j = 0; j < KC; ++j) {
-        const float h = nq_tanh(acc[0][j]);
-        const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
-        const float g2 = fmaf(acc[1][j], acc[1][j], fmaf(acc[2][j], acc[2][j], acc[3][j] * acc[3][j]));
-        acc[4][j] = fmaf(tp, acc[4][j], tpp * g2);
-        acc[1][j] *= tp; acc[2][j] *= tp; acc[3][j] *= tp;
-        acc[0][j] = h;
-      }
-      // the operand buffer of this half is still being read by the previous pass's MMAs
-      if (p == 1) { mbar_wait(bar0, phase0); phase0 ^= 1; }
-      // ---- hi/lo split, store as UMMA K-major core matrices [k/4][row][k%4] ---------------------------
-      {
-        uint8_t* buf = Abuf + half * A_BUF + row * 16;
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-#pragma unroll
-          for (int v = 0; v < KC / 4; ++v) {
-            float4 hi4, lo4;
-            split_tf32(acc[c][4 * v + 0], hi4.x, lo4.x);
-            split_tf32(acc[c][4 * v + 1], hi4.y, lo4.y);
-            split_tf32(acc[c][4 * v + 2], hi4.z, lo4.z);
-            split_tf32(acc[c][4 * v + 3], hi4.w, lo4.w);
-            *reinterpret_cast<float4*>(buf + (c * 2 + 0) * A_CHUNK + v * A_K4) = hi4;
-            *reinterpret_cast<float4*>(buf + (c * 2 + 1) * A_CHUNK + v * A_K4) = lo4;
-          }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-     }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      // ---- layer 2 on the tensor cores ---------------------------------------------------------------
-      if (tid == TCW) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          const int kchunk = 2 * hh + p;                       // hidden units 32*hh + 16*p ..
-#pragma unroll 1
-          for (int c = 0; c < CH; ++c) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(c * H);
-#pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-              const uint32_t a_hi = a_base + hh * A_BUF + (c * 2 + 0) * A_CHUNK + ks * 2 * A_K4;
-              const uint32_t a_lo = a_base + hh * A_BUF + (c * 2 + 1) * A_CHUNK + ks * 2 * A_K4;
-              const uint32_t kb = (uint32_t)((kchunk * (KC / 4) + ks * 2) * B_K4);
-              const uint64_t dah = umma_desc(a_hi, A_K4, 128), dal = umma_desc(a_lo, A_K4, 128);
-              const uint64_t dbh = umma_desc(bhi_base + kb, B_K4, 128), dbl = umma_desc(blo_base + kb, B_K4, 128);
-              const uint32_t first = (p == 0 && hh == 0 && ks == 0) ? 0u : 1u;
-              umma_tf32(d_tmem, dah, dbh, first);
-              umma_tf32(d_tmem, dal, dbh, 1u);
-              umma_tf32(d_tmem, dah, dbl, 1u);
-            }
-          }
-        }
-        umma_commit(p == 0 ? bar0 : bar1);
-      }
+    const int64_t next = item + n_chunks;
+    float xn = 0.f, yn = 0.f, zn = 0.f;
+    if (worker && next < n_items) load_xyz(next, xn, yn, zn);        // prefetch: consumed after the second MMA batch
+    // ---- pass 0: stage operands, start the MMAs --------------------------------------------------------
+    if (worker) store_operand(my_buf, acc);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == TCW / 32) issue_pass<0>(tmem_base, a_base, bhi_base, blo_base, bar0);
+    // ---- pass 1: layer 1 overlaps the pass-0 MMAs ---------------------------------------------------------
+    if (worker) {
+      layer1_pass(s, W1s, b1s, x, y, z, j_own + KC, acc);
+      mbar_wait(bar0, phase0);                                       // operand buffers free again
+      phase0 ^= 1;
+      store_operand(my_buf, acc);
     }
-    // ---- epilogue: wait for the accumulators, activation rules, output layer --------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == TCW / 32) issue_pass<1>(tmem_base, a_base, bhi_base, blo_base, bar1);
+    // ---- pass 0 of the next tile overlaps the pass-1 MMAs ---------------------------------------------------
     float out[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (worker) {
-    mbar_wait(bar1, phase1);
-    phase1 ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      if (next < n_items) layer1_pass(s, W1s, b1s, xn, yn, zn, j_own, acc);
+      x = xn; y = yn; z = zn;
+      // ---- epilogue: accumulators -> activation rules -> output layer ------------------------------------
+      mbar_wait(bar1, phase1);
+      phase1 ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 #pragma unroll 1
-    for (int sub = 0; sub < 2; ++sub) {
-      const int c0 = 32 * half + 16 * sub;                    // first hidden unit of this 16-column slice
-      float v[CH][16];
+      for (int sub = 0; sub < EPC / 8; ++sub) {
+        const int c0 = EPC * quarter + 8 * sub;                     // first hidden unit of this 8-column slice
+        float v[CH][8];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) tmem_ld16(tmem_base + lane_base + (uint32_t)(c * H + c0), v[c]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c = 0; c < CH; ++c) tmem_ld8(tmem_base + lane_base + (uint32_t)(c * H + c0), v[c]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float h = nq_tanh(v[0][j] + b2s[c0 + j]);
-        const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
-        const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
-        const float w3 = W3s[c0 + j], w3tp = w3 * tp;
-        out[0] = fmaf(w3, h, out[0]);
-        out[1] = fmaf(w3tp, v[1][j], out[1]);
-        out[2] = fmaf(w3tp, v[2][j], out[2]);
-        out[3] = fmaf(w3tp, v[3][j], out[3]);
-        out[4] = fmaf(w3, fmaf(tp, v[4][j], tpp * g2), out[4]);
+        for (int j = 0; j < 8; ++j) {
+          const float h = nq_tanh(v[0][j] + b2s[c0 + j]);
+          const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
+          const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
+          const float w3 = W3s[c0 + j], w3tp = w3 * tp;
+          out[0] = fmaf(w3, h, out[0]);
+          out[1] = fmaf(w3tp, v[1][j], out[1]);
+          out[2] = fmaf(w3tp, v[2][j], out[2]);
+          out[3] = fmaf(w3tp, v[3][j], out[3]);
+          out[4] = fmaf(w3, fmaf(tp, v[4][j], tpp * g2), out[4]);
+        }
       }
-    }
-    if (half == 1) {
+      if (quarter != 0) {
 #pragma unroll
-      for (int c = 0; c < CH; ++c) outS[row * CH + c] = out[c];
-    }
+        for (int c = 0; c < CH; ++c) outS[((quarter - 1) * ROWS + row) * CH + c] = out[c];
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                          // accumulators are free; half-1 partials visible
-    if (worker && half == 0) {
+    if (worker && quarter == 0) {
       const int64_t wr = w0 + row;
       if (wr < W) {
         const int ent = ent_index(s, spin, i, korb);
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-          phi[((int64_t)c * s.n_ent + ent) * W + wr] = out[c] + outS[row * CH + c] + (c == 0 ? b3 : 0.f);
+        for (int c = 0; c < CH; ++c) {
+          float o = out[c] + (c == 0 ? b3 : 0.f);
+#pragma unroll
+          for (int q = 0; q < NQ - 1; ++q) o += outS[(q * ROWS + row) * CH + c];
+          phi[((int64_t)c * s.n_ent + ent) * W + wr] = o;
+        }
       }
     }
-    __syncthreads();                                          // outS reusable
+    // outS is rewritten only after the next tile's two barriers, so no extra barrier is needed here
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
