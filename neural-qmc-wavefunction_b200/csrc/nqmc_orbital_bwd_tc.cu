@@ -2,20 +2,23 @@
 // hidden width 64.  Same math, interface and slab layout as orb_bwd_kernel<64,...> (nqmc_orbital.cu), which
 // stays as the FP32 FFMA parity anchor.
 //
-// Per 128-row tile (128 consecutive walkers, one electron of the network's spin), with seed = weight * inv:
+// Per 128-row tile (128 consecutive walkers, one electron of the network's spin), seed = weight * inv:
 //     h1 = tanh(f W1 + b1)                      FP32 FFMA, thread-per-row (K = 3+2A is tiny)
-//     U2 = h1 W2                                UMMA   M=128 rows, N=64, K=64     (A,B K-major)
+//     U2 = h1 W2                                UMMA  M=128 rows, N=64, K=64    A: h1 in TENSOR MEMORY, B: W2 smem
 //     h2 = tanh(U2 + b2); dW3 += seed h2; delta2 = seed W3 (1-h2^2)
-//     D1 = delta2 W2^T                          UMMA   M=128 rows, N=64, K=64     (B = the same W2 buffer, MN-major)
-//     G2 += [h1 | 1]^T delta2                   UMMA   M=128 (64 units + a ones row -> db2), N=64, K=128 rows
+//     D1 = delta2 W2^T                          UMMA  M=128 rows, N=64, K=64    A: delta2 in TMEM,      B: W2^T smem
+//     G2 += [h1 | 1]^T delta2                   UMMA  M=128 (64 units + ones -> db2), N=64, K=128 rows  (smem x smem)
 //     delta1 = D1 (1-h1^2)
-//     G1 += [f | 1]^T delta1                    UMMA   M=128 (F features + a ones row -> db1), N=64, K=128 rows
-// G2 / G1 stay in tensor memory for the whole kernel and are read back once.
+//     G1 += [f | 1]^T delta1                    UMMA  M=128 (F features + ones -> db1), N=64, K=128 rows (smem x smem)
+// G2 / G1 accumulate in tensor memory for the whole kernel and are read back once.
 //
-// Operand staging: a buffer [k/4][row][k%4] (16-byte granules) is at the same time
-//   * a K-major  no-swizzle UMMA operand with M/N = row : LBO = 2048 B (next k/4 group), SBO = 128 B (next 8 rows)
-//   * an MN-major no-swizzle UMMA operand with K   = row : SBO = 2048 B (next 4 M/N),    LBO = 128 B (next 8 rows)
-// so h1 and delta2/delta1 are split into tf32 hi/lo and stored ONCE, then consumed by two GEMMs each.
+// Operand layouts.  tf32 operands may only be MN-major in a special swizzled format, so every shared-memory
+// operand here is K-major, no swizzle: element (mn, k) at (k/4)*LBO + mn*16 + (k%4)*4 bytes, SBO = 128.
+//   * "row" operands of U2 / D1 (A[m=row][k=unit]) are written by their owning thread straight into TMEM
+//     (tcgen05.st, lane = row): no shared-memory traffic at all for them.
+//   * "K = row" operands of G2 / G1 need 4 consecutive rows of one unit in a 16-byte granule: a thread owns
+//     one row, so the 4 lanes of a quad transpose their 4x4 blocks with two butterfly shuffle stages
+//     (4 SHFL per block) before the hi/lo split; features go through a small [feature][row] staging array.
 #include <cstdlib>
 
 #include "nqmc_internal.cuh"
@@ -28,42 +31,62 @@ constexpr int TCW = 128 * NQ;         // worker threads
 constexpr int TCT = TCW + 32;         // + MMA issuer warp
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
-constexpr uint32_t TMEM_COLS = 256;   // U2 | D1 | G2 | G1, 64 columns each
-constexpr int GRP = ROWS * 16;        // one k/4 group: 128 rows x 16 B = 2048
-constexpr int HB = 17 * GRP;          // h1 hi (or lo): 16 groups + the ones group            = 34816
-constexpr int FB = 9 * GRP;           // features hi (or lo): up to 35 features + ones         = 18432
-constexpr int DB = 16 * GRP;          // delta hi (or lo)                                     = 32768
-constexpr int WB = (H / 4) * H * 16;  // W2 hi (or lo): [k/4][j][k%4]                         = 16384
-constexpr int OFF_HH = 0, OFF_HL = HB, OFF_FH = 2 * HB, OFF_FL = 2 * HB + FB, OFF_DH = 2 * HB + 2 * FB,
-              OFF_DL = OFF_DH + DB, OFF_WH = OFF_DL + DB, OFF_WL = OFF_WH + WB, OFF_MISC = OFF_WL + WB;
-constexpr int MISC_FLOATS = 35 * H + 3 * H + 3 * H + 8;   // W1, b1, b2, W3, reduction scratch
-constexpr int SMEM_BYTES = OFF_MISC + MISC_FLOATS * 4 + 64;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G2 = 128, C_G1 = 192, C_AH = 256, C_AL = 320;
+constexpr int RGH = (H + 1) * 16;     // row-group stride of the transposed h1 buffer: 64 units + the ones unit = 1040 B
+constexpr int RGD = H * 16;           // row-group stride of the transposed delta buffer                          = 1024 B
+constexpr int NRG = ROWS / 4;         // 32 row groups (granule = 4 consecutive rows of one unit)
+constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                                                   = 16384 B
+
+struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
+  int hT_hi, hT_lo, dT_hi, dT_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
+  int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the feature buffer
+};
+__host__ __device__ inline SmemMap make_map(int F) {
+  SmemMap m;
+  m.n_fu = 4 * ((F + 1 + 3) / 4);
+  m.rgf = m.n_fu * 16;
+  int o = 0;
+  m.fT_hi = o; o += NRG * m.rgf;
+  m.fT_lo = o; o += NRG * m.rgf;
+  m.hT_hi = o; o += NRG * RGH;
+  m.hT_lo = o; o += NRG * RGH;
+  m.dT_hi = o; o += NRG * RGD;
+  m.dT_lo = o; o += NRG * RGD;
+  m.wa_hi = o; o += WB;
+  m.wa_lo = o; o += WB;
+  m.wb_hi = o; o += WB;
+  m.wb_lo = o; o += WB;
+  m.fstage = o; o += m.n_fu * ROWS * 4;
+  m.misc = o; o += (F * H + 3 * H + H + 8) * 4 + 64;
+  m.total = o;
+  return m;
+}
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// D=f32, A=B=tf32, N=64, M=128; bit 15 / 16: A / B is MN-major
-constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-constexpr uint32_t IDESC_KM = IDESC_KK | (1u << 16);
-constexpr uint32_t IDESC_MM = IDESC_KK | (1u << 15) | (1u << 16);
+// D=f32, A=B=tf32, both K-major, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
-                                     uint32_t leader) {
+// A and B from shared memory
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred p, l;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 l, %5, 0;\n\t"
       "@l tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(leader)
       : "memory");
 }
-// D (+)= A B with 3xTF32: hi.hi + lo.hi + hi.lo
-__device__ __forceinline__ void umma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
-                                      uint32_t accumulate, uint32_t leader) {
-  umma(d, ah, bh, idesc, accumulate, leader);
-  umma(d, al, bh, idesc, 1u, leader);
-  umma(d, ah, bl, idesc, 1u, leader);
+// A from tensor memory, B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, l;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 l, %5, 0;\n\t"
+      "@l tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(leader)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
@@ -97,21 +120,57 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
   lo = a - hi;
 }
-// 16 consecutive k of one row -> 4 granules of the hi and lo buffers
-__device__ __forceinline__ void store16(uint8_t* hi_base, uint8_t* lo_base, const float (&v)[16]) {
+
+// 16 values of this thread's row -> tf32 hi / lo in the TMEM A-operand columns (lane = row)
+__device__ __forceinline__ void stage_rows_tmem(uint32_t t_hi, uint32_t t_lo, const float (&v)[16]) {
+  uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int j = 0; j < 16; ++j) {
+    float h, l;
+    split_tf32(v[j], h, l);
+    hi[j] = __float_as_uint(h);
+    lo[j] = __float_as_uint(l);
+  }
+  tmem_st16(t_hi, hi);
+  tmem_st16(t_lo, lo);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 4x4 transpose across the 4 lanes of a quad (two butterfly stages), then hi/lo split and one 16-byte store per
+// unit: on return the granule (rows row0..row0+3 of unit c0 + 4u + (lane & 3)) is in the transposed buffers.
+__device__ __forceinline__ void stage_cols_smem(uint8_t* hi_rg, uint8_t* lo_rg, const int c0, const int t,
+                                                const float (&v)[16]) {
+  const bool odd = t & 1, upper = t & 2;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float x0 = v[4 * u], x1 = v[4 * u + 1], x2 = v[4 * u + 2], x3 = v[4 * u + 3];
+    // stage 1 (partner t^1): 2x2 blocks
+    const float s0 = odd ? x0 : x1, s1 = odd ? x2 : x3;
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const float y0 = odd ? r0 : x0, y1 = odd ? x1 : r0, y2 = odd ? r1 : x2, y3 = odd ? x3 : r1;
+    // stage 2 (partner t^2): swap the off-diagonal 2-element blocks
+    const float q0 = upper ? y0 : y2, q1 = upper ? y1 : y3;
+    const float p0 = __shfl_xor_sync(0xffffffffu, q0, 2), p1 = __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float z0 = upper ? p0 : y0, z1 = upper ? p1 : y1, z2 = upper ? y2 : p0, z3 = upper ? y3 : p1;
     float4 h4, l4;
-    split_tf32(v[4 * g + 0], h4.x, l4.x);
-    split_tf32(v[4 * g + 1], h4.y, l4.y);
-    split_tf32(v[4 * g + 2], h4.z, l4.z);
-    split_tf32(v[4 * g + 3], h4.w, l4.w);
-    *reinterpret_cast<float4*>(hi_base + g * GRP) = h4;
-    *reinterpret_cast<float4*>(lo_base + g * GRP) = l4;
+    split_tf32(z0, h4.x, l4.x);
+    split_tf32(z1, h4.y, l4.y);
+    split_tf32(z2, h4.z, l4.z);
+    split_tf32(z3, h4.w, l4.w);
+    const int unit = c0 + 4 * u + t;
+    *reinterpret_cast<float4*>(hi_rg + unit * 16) = h4;
+    *reinterpret_cast<float4*>(lo_rg + unit * 16) = l4;
   }
 }
 
@@ -121,14 +180,17 @@ __global__ void __launch_bounds__(TCT, 1)
                       const float* __restrict__ e_l, const int64_t W, float* __restrict__ part, const int n_chunks,
                       const int p_mlp) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float* misc = reinterpret_cast<float*>(smem + OFF_MISC);
+  const int F = s.F, A = s.A;
+  const SmemMap mp = make_map(F);
+  float* misc = reinterpret_cast<float*>(smem + mp.misc);
   float* W1s = misc;                 // [F][H]
-  float* b1s = W1s + 35 * H;
+  float* b1s = W1s + F * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
-  float* redS = W3s + H;             // [3H + 8]: dW3[H], (spare), db3
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + MISC_FLOATS);   // 3 mbarriers
+  float* redS = W3s + H;             // [H + 8]: dW3[H], db3
+  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + H + 8);   // 3 mbarriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* fstage = reinterpret_cast<float*>(smem + mp.fstage);   // [n_fu][ROWS]
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (ROWS - 1), quarter = (tid >> 7) & (NQ - 1);
@@ -139,29 +201,33 @@ __global__ void __launch_bounds__(TCT, 1)
   const int ns = spin == 0 ? s.n_up : s.n_dn;
   const int elec0 = spin == 0 ? 0 : s.n_up;
   const MlpOff off = s.mlp[m];
-  const int F = s.F, A = s.A;
-  const int n_fgrp = (F + 1 + 3) / 4;            // feature granules including the ones column
 
   // ---- setup ----------------------------------------------------------------------------------------------
+  for (int idx = tid; idx < mp.wa_hi / 16; idx += TCT) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = tid; idx < mp.n_fu * ROWS; idx += TCT) fstage[idx] = 0.f;
   for (int idx = tid; idx < F * H; idx += TCT) W1s[idx] = theta[off.W1 + idx];
   for (int q = tid; q < H; q += TCT) {
     b1s[q] = theta[off.b1 + q];
     b2s[q] = theta[off.b2 + q];
     W3s[q] = theta[off.W3 + q];
   }
-  for (int q = tid; q < 3 * H + 8; q += TCT) redS[q] = 0.f;
-  for (int idx = tid; idx < H * H; idx += TCT) {           // W2 -> [k/4][j][k%4], hi / lo
+  for (int q = tid; q < H + 8; q += TCT) redS[q] = 0.f;
+  for (int idx = tid; idx < H * H; idx += TCT) {
     const int k = idx / H, j = idx % H;
     float hi, lo;
     split_tf32(theta[off.W2 + idx], hi, lo);
-    const int o = (k >> 2) * (H * 4) + j * 4 + (k & 3);
-    reinterpret_cast<float*>(smem + OFF_WH)[o] = hi;
-    reinterpret_cast<float*>(smem + OFF_WL)[o] = lo;
+    // copy a: B[n=j][kk=k] (for U2 = h1 W2)      -> [k/4][j][k%4]
+    const int oa = (k >> 2) * (H * 4) + j * 4 + (k & 3);
+    reinterpret_cast<float*>(smem + mp.wa_hi)[oa] = hi;
+    reinterpret_cast<float*>(smem + mp.wa_lo)[oa] = lo;
+    // copy b: B[n=k][kk=j] (for D1 = delta2 W2^T) -> [j/4][k][j%4]
+    const int ob = (j >> 2) * (H * 4) + k * 4 + (j & 3);
+    reinterpret_cast<float*>(smem + mp.wb_hi)[ob] = hi;
+    reinterpret_cast<float*>(smem + mp.wb_lo)[ob] = lo;
   }
-  // zero the operand buffers once (unused feature granules / rows must hold finite values), then the ones group of h1
-  for (int idx = tid; idx < (OFF_WH) / 16; idx += TCT) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  if (tid < ROWS) *reinterpret_cast<float4*>(smem + OFF_HH + 16 * GRP + tid * 16) = make_float4(1.f, 0.f, 0.f, 0.f);
+  // the ones unit (index 64) of the transposed h1 buffer -> row 64 of G2 = db2 ; hi = 1, lo stays 0
+  for (int g = tid; g < NRG; g += TCT) *reinterpret_cast<float4*>(smem + mp.hT_hi + g * RGH + H * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
   if (tid == 0) {
     for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,7 +242,6 @@ __global__ void __launch_bounds__(TCT, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t T_U2 = tmem_base, T_D1 = tmem_base + 64, T_G2 = tmem_base + 128, T_G1 = tmem_base + 192;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_u = smem_u32(&bars[0]), bar_d = smem_u32(&bars[1]), bar_g = smem_u32(&bars[2]);
   uint32_t ph_u = 0, ph_d = 0, ph_g = 0;
@@ -188,11 +253,12 @@ __global__ void __launch_bounds__(TCT, 1)
   for (int j = 0; j < UPT; ++j) gW3[j] = 0.f;
   float gb3 = 0.f;
   const int c0 = UPT * quarter;                     // first hidden unit / output column of this thread
+  const int t4 = tid & 3;                           // position inside the lane quad == row % 4
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  uint8_t* my_h_hi = smem + OFF_HH + (c0 / 4) * GRP + row * 16;
-  uint8_t* my_h_lo = smem + OFF_HL + (c0 / 4) * GRP + row * 16;
-  uint8_t* my_d_hi = smem + OFF_DH + (c0 / 4) * GRP + row * 16;
-  uint8_t* my_d_lo = smem + OFF_DL + (c0 / 4) * GRP + row * 16;
+  uint8_t* hT_hi = smem + mp.hT_hi + (row >> 2) * RGH;
+  uint8_t* hT_lo = smem + mp.hT_lo + (row >> 2) * RGH;
+  uint8_t* dT_hi = smem + mp.dT_hi + (row >> 2) * RGD;
+  uint8_t* dT_lo = smem + mp.dT_lo + (row >> 2) * RGD;
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
@@ -216,11 +282,8 @@ __global__ void __launch_bounds__(TCT, 1)
       }
       seed = wt * inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
       if (!valid || !isfinite(seed)) seed = 0.f;
-      // the previous tile's G2 / G1 MMAs still read the h1 / feature / delta buffers
-      if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
-      float feat[36];                                  // indexed only with compile-time-unrollable loops below
       const float pc[3] = {x, y, z};
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -233,26 +296,22 @@ __global__ void __launch_bounds__(TCT, 1)
           h1[4 * v + 3] = fmaf(pc[d], wv.w, h1[4 * v + 3]);
         }
       }
-      // feature granules are written by the thread whose quarter matches granule % 4; coordinates first
-      float* f_hi = reinterpret_cast<float*>(smem + OFF_FH) + row * 4;
-      float* f_lo = reinterpret_cast<float*>(smem + OFF_FL) + row * 4;
-      auto put_feature = [&](int f, float val) {         // feature f of this row -> granule f/4, slot f%4
-        if (((f >> 2) & (NQ - 1)) == quarter) {
-          float hi, lo;
-          split_tf32(val, hi, lo);
-          f_hi[(f >> 2) * (GRP / 4) + (f & 3)] = hi;
-          f_lo[(f >> 2) * (GRP / 4) + (f & 3)] = lo;
-        }
-      };
-      put_feature(0, x);
-      put_feature(1, y);
-      put_feature(2, z);
+      // the previous tile's G1 reads the feature / delta buffers, its G2 the transposed h1 buffer
+      if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }
+      if (quarter == 0) {
+        fstage[0 * ROWS + row] = x;
+        fstage[1 * ROWS + row] = y;
+        fstage[2 * ROWS + row] = z;
+        fstage[F * ROWS + row] = 1.0f;                  // ones unit -> db1
+      }
       for (int a = 0; a < A; ++a) {
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
         const float ex = __expf(-dd);
-        put_feature(3 + a, dd);
-        put_feature(3 + A + a, ex);
+        if (quarter == 0) {
+          fstage[(3 + a) * ROWS + row] = dd;
+          fstage[(3 + A + a) * ROWS + row] = ex;
+        }
 #pragma unroll
         for (int v = 0; v < UPT / 4; ++v) {
           const float4 wd = *reinterpret_cast<const float4*>(W1s + (3 + a) * H + c0 + 4 * v);
@@ -263,36 +322,49 @@ __global__ void __launch_bounds__(TCT, 1)
           h1[4 * v + 3] = fmaf(dd, wd.w, fmaf(ex, we.w, h1[4 * v + 3]));
         }
       }
-      put_feature(F, 1.0f);                             // ones column -> db1
-      (void)feat;
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
-      store16(my_h_hi, my_h_lo, h1);
+      stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
+      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- U2 = h1 W2 ------------------------------------------------------------------------------------------
+    // ---- U2 = h1 W2 (A from tensor memory) ------------------------------------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
-      const uint64_t ah = umma_desc(sbase + OFF_HH, GRP, 128), al = umma_desc(sbase + OFF_HL, GRP, 128);
-      const uint64_t bh = umma_desc(sbase + OFF_WH, H * 16, 128), bl = umma_desc(sbase + OFF_WL, H * 16, 128);
+      const uint64_t bh = umma_desc(sbase + mp.wa_hi, H * 16, 128), bl = umma_desc(sbase + mp.wa_lo, H * 16, 128);
 #pragma unroll
       for (int ks = 0; ks < H / 8; ++ks) {
-        const uint64_t ao = (uint64_t)((ks * 2 * GRP) >> 4), bo = (uint64_t)((ks * 2 * H * 16) >> 4);
-        umma3(T_U2, ah + ao, al + ao, bh + bo, bl + bo, IDESC_KK, ks == 0 ? 0u : 1u, leader);
+        const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+        const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
+        umma_ts(tmem_base + C_U2, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+        umma_ts(tmem_base + C_U2, al, bh + bo, 1u, leader);
+        umma_ts(tmem_base + C_U2, ah, bl + bo, 1u, leader);
       }
       umma_commit(bar_u, leader);
       __syncwarp();
     }
-    // ---- h2, dW3, delta2 ---------------------------------------------------------------------------------------
+    // ---- feature relayout (for G1), then h2, dW3, delta2 ------------------------------------------------------------
     if (worker) {
+      // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
+      for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
+        const int f = idx / NRG, g = idx % NRG;
+        const float4 fv = *reinterpret_cast<const float4*>(fstage + f * ROWS + 4 * g);
+        float4 h4, l4;
+        split_tf32(fv.x, h4.x, l4.x);
+        split_tf32(fv.y, h4.y, l4.y);
+        split_tf32(fv.z, h4.z, l4.z);
+        split_tf32(fv.w, h4.w, l4.w);
+        *reinterpret_cast<float4*>(smem + mp.fT_hi + g * mp.rgf + f * 16) = h4;
+        *reinterpret_cast<float4*>(smem + mp.fT_lo + g * mp.rgf + f * 16) = l4;
+      }
       mbar_wait(bar_u, ph_u);
       ph_u ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float v[16];
-      tmem_ld16(T_U2 + lane_base + (uint32_t)c0, v);
+      tmem_ld16(tmem_base + lane_base + C_U2 + (uint32_t)c0, v);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         const float h = nq_tanh(v[j] + b2s[c0 + j]);
@@ -300,33 +372,37 @@ __global__ void __launch_bounds__(TCT, 1)
         v[j] = seed * W3s[c0 + j] * fmaf(-h, h, 1.0f);
       }
       if (quarter == 0) gb3 += seed;
-      store16(my_d_hi, my_d_lo, v);
+      stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, v);
+      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- D1 = delta2 W2^T ; G2 += [h1|1]^T delta2 ------------------------------------------------------------------
+    // ---- D1 = delta2 W2^T (A from tensor memory) ; G2 += [h1|1]^T delta2 ---------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       {
-        const uint64_t ah = umma_desc(sbase + OFF_DH, GRP, 128), al = umma_desc(sbase + OFF_DL, GRP, 128);
-        // B[n = k][kk = j] = W2[k][j]: MN-major view of the W2 buffer: SBO = 1024 B (next 4 k), LBO = 128 B (next 8 j)
-        const uint64_t bh = umma_desc(sbase + OFF_WH, 128, H * 16), bl = umma_desc(sbase + OFF_WL, 128, H * 16);
+        const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
 #pragma unroll
         for (int ks = 0; ks < H / 8; ++ks) {
-          const uint64_t ao = (uint64_t)((ks * 2 * GRP) >> 4), bo = (uint64_t)((ks * 128) >> 4);
-          umma3(T_D1, ah + ao, al + ao, bh + bo, bl + bo, IDESC_KM, ks == 0 ? 0u : 1u, leader);
+          const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+          const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
+          umma_ts(tmem_base + C_D1, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+          umma_ts(tmem_base + C_D1, al, bh + bo, 1u, leader);
+          umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
         }
       }
       {
-        // A[m = unit][kk = row] (MN-major view of the h1 buffer), B[n = j][kk = row] (MN-major view of the delta buffer)
-        const uint64_t ah = umma_desc(sbase + OFF_HH, 128, GRP), al = umma_desc(sbase + OFF_HL, 128, GRP);
-        const uint64_t bh = umma_desc(sbase + OFF_DH, 128, GRP), bl = umma_desc(sbase + OFF_DL, 128, GRP);
+        const uint64_t ah = umma_desc(sbase + mp.hT_hi, RGH, 128), al = umma_desc(sbase + mp.hT_lo, RGH, 128);
+        const uint64_t bh = umma_desc(sbase + mp.dT_hi, RGD, 128), bl = umma_desc(sbase + mp.dT_lo, RGD, 128);
 #pragma unroll
         for (int ks = 0; ks < ROWS / 8; ++ks) {
-          const uint64_t o = (uint64_t)((ks * 128) >> 4);
-          umma3(T_G2, ah + o, al + o, bh + o, bl + o, IDESC_MM, (first_tile && ks == 0) ? 0u : 1u, leader);
+          const uint64_t ao = (uint64_t)((ks * 2 * RGH) >> 4), bo = (uint64_t)((ks * 2 * RGD) >> 4);
+          const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
+          umma_ss(tmem_base + C_G2, ah + ao, bh + bo, acc, leader);
+          umma_ss(tmem_base + C_G2, al + ao, bh + bo, 1u, leader);
+          umma_ss(tmem_base + C_G2, ah + ao, bl + bo, 1u, leader);
         }
       }
       umma_commit(bar_d, leader);
@@ -338,10 +414,10 @@ __global__ void __launch_bounds__(TCT, 1)
       ph_d ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float v[16];
-      tmem_ld16(T_D1 + lane_base + (uint32_t)c0, v);
+      tmem_ld16(tmem_base + lane_base + C_D1 + (uint32_t)c0, v);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) v[j] *= fmaf(-h1[j], h1[j], 1.0f);
-      store16(my_d_hi, my_d_lo, v);                     // delta2 is dead: both of its GEMMs have completed
+      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);        // delta2^T is dead: G2 has completed
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -350,12 +426,15 @@ __global__ void __launch_bounds__(TCT, 1)
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
-      const uint64_t ah = umma_desc(sbase + OFF_FH, 128, GRP), al = umma_desc(sbase + OFF_FL, 128, GRP);
-      const uint64_t bh = umma_desc(sbase + OFF_DH, 128, GRP), bl = umma_desc(sbase + OFF_DL, 128, GRP);
+      const uint64_t ah = umma_desc(sbase + mp.fT_hi, mp.rgf, 128), al = umma_desc(sbase + mp.fT_lo, mp.rgf, 128);
+      const uint64_t bh = umma_desc(sbase + mp.dT_hi, RGD, 128), bl = umma_desc(sbase + mp.dT_lo, RGD, 128);
 #pragma unroll
       for (int ks = 0; ks < ROWS / 8; ++ks) {
-        const uint64_t o = (uint64_t)((ks * 128) >> 4);
-        umma3(T_G1, ah + o, al + o, bh + o, bl + o, IDESC_MM, (first_tile && ks == 0) ? 0u : 1u, leader);
+        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgf) >> 4), bo = (uint64_t)((ks * 2 * RGD) >> 4);
+        const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
+        umma_ss(tmem_base + C_G1, ah + ao, bh + bo, acc, leader);
+        umma_ss(tmem_base + C_G1, al + ao, bh + bo, 1u, leader);
+        umma_ss(tmem_base + C_G1, ah + ao, bl + bo, 1u, leader);
       }
       umma_commit(bar_g, leader);
       __syncwarp();
@@ -367,49 +446,45 @@ __global__ void __launch_bounds__(TCT, 1)
   float* slab = part + (int64_t)blockIdx.x * p_mlp;
   const int o_b1 = 0, o_W1 = H, o_b2 = H + F * H, o_W2 = o_b2 + H, o_b3 = o_W2 + H * H, o_W3 = o_b3 + 1;
   if (worker) {
-    if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // thread (row = TMEM lane, quarter): 16 columns of lane `row` of G2 and G1
-    float v[16];
+    float v2[16], v1[16];
     if (!first_tile) {
-      tmem_ld16(T_G2 + lane_base + (uint32_t)c0, v);
-      if (row < H) {
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) slab[o_W2 + row * H + c0 + j] = v[j];
-      } else if (row == H) {
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) slab[o_b2 + c0 + j] = v[j];
-      }
-      tmem_ld16(T_G1 + lane_base + (uint32_t)c0, v);
-      if (row < F) {
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) slab[o_W1 + row * H + c0 + j] = v[j];
-      } else if (row == F) {
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) slab[o_b1 + c0 + j] = v[j];
-      }
+      mbar_wait(bar_g, ph_g);
+      ph_g ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)c0, v2);   // lane = h1 unit (row 64: ones -> db2)
+      tmem_ld16(tmem_base + lane_base + C_G1 + (uint32_t)c0, v1);   // lane = feature   (row F : ones -> db1)
     } else {
-      // this CTA had no tile: its slab must still be defined
-      if (row < H) for (int j = 0; j < UPT; ++j) slab[o_W2 + row * H + c0 + j] = 0.f;
-      if (row == H) for (int j = 0; j < UPT; ++j) slab[o_b2 + c0 + j] = 0.f;
-      if (row < F) for (int j = 0; j < UPT; ++j) slab[o_W1 + row * H + c0 + j] = 0.f;
-      if (row == F) for (int j = 0; j < UPT; ++j) slab[o_b1 + c0 + j] = 0.f;
-    }
-    // dW3 / db3: reduce the per-row partials over the 128 rows
 #pragma unroll
-    for (int j = 0; j < UPT; ++j) {
-      float t = warp_sum(gW3[j]);
+      for (int j = 0; j < UPT; ++j) v2[j] = v1[j] = 0.f;             // this CTA had no tile: the slab must still be defined
+    }
+    if (row < H) {
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) slab[o_W2 + row * H + c0 + j] = v2[j];
+    } else if (row == H) {
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) slab[o_b2 + c0 + j] = v2[j];
+    }
+    if (row < F) {
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) slab[o_W1 + row * H + c0 + j] = v1[j];
+    } else if (row == F) {
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) slab[o_b1 + c0 + j] = v1[j];
+    }
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) {                     // dW3 / db3: reduce the per-row partials over the 128 rows
+      const float t = warp_sum(gW3[j]);
       if ((tid & 31) == 0) atomicAdd(&redS[c0 + j], t);
     }
     if (quarter == 0) {
-      float t = warp_sum(gb3);
-      if ((tid & 31) == 0) atomicAdd(&redS[3 * H], t);
+      const float t = warp_sum(gb3);
+      if ((tid & 31) == 0) atomicAdd(&redS[H], t);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   for (int q = tid; q < H; q += TCT) slab[o_W3 + q] = redS[q];
-  if (tid == 0) slab[o_b3] = redS[3 * H];
+  if (tid == 0) slab[o_b3] = redS[H];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
@@ -420,11 +495,14 @@ __global__ void __launch_bounds__(TCT, 1)
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                          int* n_chunks_out, cudaStream_t st) {
   const DevSys& s = ctx->sys;
-  if (s.H != H || s.F > 34) return NQMC_ERR_UNSUPPORTED;
-  if (getenv("NQMC_TC_BWD") == nullptr) return NQMC_ERR_UNSUPPORTED;   // work in progress: off unless requested
+  if (s.H != H) return NQMC_ERR_UNSUPPORTED;
+  const SmemMap mp = make_map(s.F);
+  if (mp.total > 227 * 1024 || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
+  if (const char* e = getenv("NQMC_TC_BWD"))
+    if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    NQMC_CUDA(cudaFuncSetAttribute(orb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NQMC_CUDA(cudaFuncSetAttribute(orb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
@@ -435,8 +513,8 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   if (n_chunks > max_items) n_chunks = (int)max_items;
   {
     ProfScope ps(ctx, NQ_PROF_BWD, st);
-    orb_bwd_tc_kernel<<<n_chunks * s.n_mlp, TCT, SMEM_BYTES, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
-                                                                   n_chunks, ctx->p_mlp);
+    orb_bwd_tc_kernel<<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
+                                                                 n_chunks, ctx->p_mlp);
   }
   NQMC_LAUNCH_CHECK();
   *n_chunks_out = n_chunks;
