@@ -746,6 +746,10 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
 int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st) {
   const int H = ctx->sys.H;
   if (channels == 1) {
+    if (ctx->use_tc) {
+      int rc = nq_launch_orb_eval1_tc(ctx, r, W, phi, st);
+      if (rc != NQMC_ERR_UNSUPPORTED) return rc;
+    }
     if (H == 32) return launch_eval_t<32, 1, 8, 256>(ctx, r, W, phi, st);
     if (H == 64) return launch_eval_t<64, 1, 8, 256>(ctx, r, W, phi, st);
     if (H == 128) return launch_eval_t<128, 1, 8, 256>(ctx, r, W, phi, st);
