@@ -51,36 +51,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The timed region lasts tens of milliseconds,
+    so NVML is polled in-process every ~1 ms (nvidia-smi -lms cannot sample that fast); falls back to one
+    nvidia-smi query when NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self._h is None:                       # fallback: one nvidia-smi sample (still under load: called before sync)
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml polled every ~1 ms during the timed steps"}
 
 
 def make_problem():
@@ -225,10 +244,17 @@ def run_ours(args):
         flops_step, flops_value = algorithmic_flops_per_walker_step(N_ATOMS, HIDDEN, mol.n_electrons)
         pk = peaks()
         ffma_peak = ctx.ffma_peak(5)
+        tf32_peak = measure_tf32_peak(dev)
+        use_tc = os.environ.get("NQMC_TC", "1") != "0"
         ms5, n5 = prof["eval5"]
         # dominant kernel: the 5-channel orbital forward (value, gradient, Laplacian): 5 * 2 m E flop per walker
         flops_launch = 5.0 * flops_value * Wl
         ach = flops_launch / (ms5 / max(n5, 1) * 1e-3) / 1e12 if n5 else None
+        F_in = 3 + 2 * N_ATOMS
+        frac_l2 = HIDDEN * HIDDEN / float(F_in * HIDDEN + HIDDEN * HIDDEN + HIDDEN)      # share of the MACs in the H x H layer
+        peak3 = tf32_peak / 3.0                                   # 3xTF32: three tensor-core products per fp32-grade product
+        # time floor of the kernel: H x H layer at the 3xTF32 tensor rate + input/output layers at the FP32 FFMA rate
+        t_floor = flops_launch * frac_l2 / (peak3 * 1e12) + flops_launch * (1 - frac_l2) / (ffma_peak * 1e12)
         value = world * Wl * args.steps / (total_ms * 1e-3)
         out = {
             "metric": "walker-steps/s", "value": value, "unit": "walker-steps/s", "n_gpus": world,
@@ -244,10 +270,20 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if world == 1
                     else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host"},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32_ffma", "kernel": "orb_eval_kernel<64,5,4,256> (orbital forward: value+grad+Laplacian)",
-                         "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ach else None,
-                         "peak_source": "measured live: nqmc_ffma_peak (register FFMA chains); MEASURED_PEAKS.json has no fp32 figure",
-                         "peak_nominal_148x128x2x1.965GHz": 74.4, "bf16_tensor_peak_measured": pk.get("bf16_tflops"),
+            "roofline": ({"bound": "tensor", "kernel": "orb_eval5_tc_kernel (orbital forward value+grad+Laplacian; H x H layer = tcgen05 3xTF32, input layer = FFMA)",
+                          "achieved": ach, "peak": peak3, "unit": "TFLOP/s", "frac": (ach / peak3) if ach else None,
+                          "peak_source": "cuBLAS TF32 GEMM 8192^3 measured live in this run, divided by 3 (3xTF32 split); "
+                                         "MEASURED_PEAKS.json has only a bf16 figure",
+                          "tf32_dense_tflops_measured": tf32_peak,
+                          "frac_of_mixed_floor": (t_floor / (ms5 / max(n5, 1) * 1e-3)) if n5 else None,
+                          "mixed_floor_note": "floor = HxH-layer flops / (tf32/3) + other-layer flops / measured FFMA peak",
+                          "frac_vs_bf16_peak": (ach / pk["bf16_tflops"]) if (ach and pk.get("bf16_tflops")) else None}
+                         if use_tc else
+                         {"bound": "fp32_ffma", "kernel": "orb_eval_kernel<64,5,4,256> (orbital forward: value+grad+Laplacian)",
+                          "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ach else None,
+                          "peak_source": "measured live: nqmc_ffma_peak (register FFMA chains)"}),
+            "roofline_context": {"ffma_peak_tflops_measured": ffma_peak, "peak_nominal_148x128x2x1.965GHz": 74.4,
+                         "bf16_tensor_peak_measured": pk.get("bf16_tflops"),
                          "hbm_gbs_measured": pk.get("hbm_gbs"), "traffic": None,
                          "whole_step_achieved_tflops": flops_step * Wl / (total_ms / args.steps * 1e-3) / 1e12,
                          "kernel_ms": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
@@ -261,6 +297,27 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def measure_tf32_peak(dev, n=8192, reps=8):
+    """Dense TF32 tensor-core throughput of this GPU (cuBLAS through torch.matmul), best of `reps`, in TFLOP/s."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(n, n, device=dev, dtype=torch.float32)
+    b = torch.randn(n, n, device=dev, dtype=torch.float32)
+    best = 0.0
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return best
 
 
 # =================================================================================================
@@ -317,7 +374,7 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers-per-gpu", type=int, default=WALKERS_PER_GPU)
