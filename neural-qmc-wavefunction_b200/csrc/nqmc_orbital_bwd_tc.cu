@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(TCT, 1)
   float* b2s = b1s + H;
   float* W3s = b2s + H;
   float* redS = W3s + H;             // [H + 8]: dW3[H], db3
-  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + H + 8);   // 3 mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + H + 8);   // 4 mbarriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* fstage = reinterpret_cast<float*>(smem + mp.fstage);   // [n_fu][ROWS]
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TCT, 1)
   // the ones unit (index 64) of the transposed h1 buffer -> row 64 of G2 = db2 ; hi = 1, lo stays 0
   for (int g = tid; g < NRG; g += TCT) *reinterpret_cast<float4*>(smem + mp.hT_hi + g * RGH + H * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
   if (tid == 0) {
-    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
+    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(TCT, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_u = smem_u32(&bars[0]), bar_d = smem_u32(&bars[1]), bar_g = smem_u32(&bars[2]);
-  uint32_t ph_u = 0, ph_d = 0, ph_g = 0;
+  const uint32_t bar_u = smem_u32(&bars[0]), bar_d = smem_u32(&bars[1]), bar_g2 = smem_u32(&bars[2]), bar_g = smem_u32(&bars[3]);
+  uint32_t ph_u = 0, ph_d = 0, ph_g2 = 0, ph_g = 0;
   float centerf = 0.f;
   if (hdr != nullptr) centerf = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
 
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TCT, 1)
   for (int64_t item = chunk; item < n_items; item += n_chunks) {
     const int i = (int)(item % ns);
     const int64_t w0 = (item / ns) * ROWS;
-    float h1[UPT], seed = 0.f;
+    float h1[UPT], d2[UPT], seed = 0.f;
     if (worker) {
       // ---- positions, seed, features, layer 1 (FP32 FFMA) --------------------------------------------------
       int64_t w = w0 + row;
@@ -296,8 +296,6 @@ __global__ void __launch_bounds__(TCT, 1)
           h1[4 * v + 3] = fmaf(pc[d], wv.w, h1[4 * v + 3]);
         }
       }
-      // the previous tile's G1 reads the feature / delta buffers, its G2 the transposed h1 buffer
-      if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }
       if (quarter == 0) {
         fstage[0 * ROWS + row] = x;
         fstage[1 * ROWS + row] = y;
@@ -324,9 +322,8 @@ __global__ void __launch_bounds__(TCT, 1)
       }
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
+      // A operand of U2: straight into tensor memory (its previous reader, D1 of the last tile, has completed)
       stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
-      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -346,8 +343,10 @@ __global__ void __launch_bounds__(TCT, 1)
       umma_commit(bar_u, leader);
       __syncwarp();
     }
-    // ---- feature relayout (for G1), then h2, dW3, delta2 ------------------------------------------------------------
+    // ---- while U2 runs: transposed h1 (for G2) and feature relayout (for G1); then h2, dW3, delta2 ----------------------
     if (worker) {
+      if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }      // the previous tile's G1 reads the feature / delta buffers
+      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);                    // its G2 (reader of this buffer) was waited for already
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
       for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
         const int f = idx / NRG, g = idx % NRG;
@@ -373,12 +372,12 @@ __global__ void __launch_bounds__(TCT, 1)
       }
       if (quarter == 0) gb3 += seed;
       stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, v);
-      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) d2[j] = v[j];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- D1 = delta2 W2^T (A from tensor memory) ; G2 += [h1|1]^T delta2 ---------------------------------------------
+    // ---- D1 = delta2 W2^T (A from tensor memory) -----------------------------------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
@@ -393,6 +392,18 @@ __global__ void __launch_bounds__(TCT, 1)
           umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
         }
       }
+      umma_commit(bar_d, leader);
+      __syncwarp();
+    }
+    // ---- while D1 runs: transposed delta2 (B operand of G2) -----------------------------------------------------------------
+    if (worker) {
+      stage_cols_smem(dT_hi, dT_lo, c0, t4, d2);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- G2 += [h1|1]^T delta2 ------------------------------------------------------------------------------------------
+    if (warp == TCW / 32) {
+      const uint32_t leader = elect_one();
       {
         const uint64_t ah = umma_desc(sbase + mp.hT_hi, RGH, 128), al = umma_desc(sbase + mp.hT_lo, RGH, 128);
         const uint64_t bh = umma_desc(sbase + mp.dT_hi, RGD, 128), bl = umma_desc(sbase + mp.dT_lo, RGD, 128);
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(TCT, 1)
           umma_ss(tmem_base + C_G2, ah + ao, bl + bo, 1u, leader);
         }
       }
-      umma_commit(bar_d, leader);
+      umma_commit(bar_g2, leader);
       __syncwarp();
     }
     // ---- delta1 = D1 (1 - h1^2) -----------------------------------------------------------------------------------
@@ -417,7 +428,9 @@ __global__ void __launch_bounds__(TCT, 1)
       tmem_ld16(tmem_base + lane_base + C_D1 + (uint32_t)c0, v);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) v[j] *= fmaf(-h1[j], h1[j], 1.0f);
-      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);        // delta2^T is dead: G2 has completed
+      mbar_wait(bar_g2, ph_g2);                        // G2 still reads delta2^T from the buffer delta1^T goes into
+      ph_g2 ^= 1;
+      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
