@@ -95,6 +95,17 @@ int64_t nqmc_leaf_info(const nqmc_ctx* ctx, int index, char* path, size_t cap, i
 int nqmc_set_params(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream stream);
 int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta_host, int64_t P, nqmc_stream stream);
 
+/* Read theta back (device-to-device / device-to-host). */
+int nqmc_get_params(nqmc_ctx* ctx, float* theta, int64_t P, nqmc_stream stream);
+int nqmc_get_params_host(nqmc_ctx* ctx, float* theta_host, int64_t P, nqmc_stream stream);
+/* Fused optimizer epilogue on the device: gradient = 2 gsum / hdr[N] (float32), global-norm clip,
+ * Adam (b1 0.9, b2 0.999, eps 1e-8), theta updated IN PLACE in the ctx.
+ * Replaces: optax.chain(clip_by_global_norm(clip), adam(lr)).update + apply_updates -- src/nqmc/optimizer/vmc.py:180-184,256-261
+ * and the grad_norm metric (:264-266).  m, v: device [P] fp32 moments, caller-owned, zero before the first step;
+ * count: 1-based step number; grad_norm: device double (pre-clip norm), may be NULL. */
+int nqmc_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,
+                   float clip, double* grad_norm, nqmc_stream stream);
+
 /* ---- layout helpers -------------------------------------------------------------------------- */
 int nqmc_aos_to_soa(nqmc_ctx* ctx, const float* aos, float* soa, int64_t W, nqmc_stream stream);
 int nqmc_soa_to_aos(nqmc_ctx* ctx, const float* soa, float* aos, int64_t W, nqmc_stream stream);

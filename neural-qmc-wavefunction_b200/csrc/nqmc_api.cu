@@ -291,6 +291,40 @@ int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stre
   return NQMC_OK;
 }
 
+int nqmc_get_params(nqmc_ctx* ctx, float* theta, int64_t P, nqmc_stream st) {
+  if (!ctx || !theta) return NQMC_ERR_ARG;
+  if (P != ctx->sys.P) {
+    ctx->err = "theta has the wrong length";
+    return NQMC_ERR_ARG;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaMemcpyAsync(theta, ctx->theta, sizeof(float) * (size_t)P, cudaMemcpyDeviceToDevice, S(st)));
+  return NQMC_OK;
+}
+
+int nqmc_get_params_host(nqmc_ctx* ctx, float* theta, int64_t P, nqmc_stream st) {
+  if (!ctx || !theta) return NQMC_ERR_ARG;
+  if (P != ctx->sys.P) {
+    ctx->err = "theta has the wrong length";
+    return NQMC_ERR_ARG;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaMemcpyAsync(theta, ctx->theta, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, S(st)));
+  NQMC_CUDA(cudaStreamSynchronize(S(st)));
+  return NQMC_OK;
+}
+
+int nqmc_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,
+                   float clip, double* grad_norm, nqmc_stream st) {
+  if (!ctx || !gsum || !hdr || !m || !v || count < 1) return NQMC_ERR_ARG;
+  if (ctx->cap_w <= 0) {
+    ctx->err = "call nqmc_reserve first";
+    return NQMC_ERR_STATE;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_adam_step(ctx, gsum, hdr, m, v, count, lr, clip, grad_norm, S(st));
+}
+
 int nqmc_aos_to_soa(nqmc_ctx* ctx, const float* aos, float* soa, int64_t W, nqmc_stream st) {
   if (!ctx || !aos || !soa || W <= 0) return NQMC_ERR_ARG;
   NQMC_CUDA(cudaSetDevice(ctx->device));

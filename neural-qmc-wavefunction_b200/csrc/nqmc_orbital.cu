@@ -679,7 +679,8 @@ int launch_eval_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStre
   const DevSys& s = ctx->sys;
   size_t smem = sizeof(float) * ((size_t)s.F * H + (size_t)H * H + 3 * H + (size_t)H * K::SJ);
   auto kern = orb_eval_kernel<H, C, RPT, NT>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
@@ -710,7 +711,8 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
   const DevSys& s = ctx->sys;
   size_t smem = sizeof(float) * K::smem_floats(s.F);
   auto kern = orb_bwd_kernel<H, NT>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;

@@ -513,7 +513,8 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   if (mp.total > 227 * 1024 || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
   if (const char* e = getenv("NQMC_TC_BWD"))
     if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(orb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;

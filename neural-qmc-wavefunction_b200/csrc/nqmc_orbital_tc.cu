@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(TCT, 1)
 int nq_launch_orb_eval5_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
   const DevSys& s = ctx->sys;
   if (s.H != H || s.F > 35) return NQMC_ERR_UNSUPPORTED;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(orb_eval5_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;

@@ -256,7 +256,8 @@ int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi,
   const DevSys& s = ctx->sys;
   if (s.H != H) return NQMC_ERR_UNSUPPORTED;
   const size_t smem = 2 * WB + ((size_t)s.F * H + 3 * H + 2 * (NQ - 1) * ROWS) * 4 + 64;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(orb_eval1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;

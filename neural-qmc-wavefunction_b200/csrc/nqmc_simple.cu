@@ -268,7 +268,8 @@ static int simple_launch_eval(nqmc_ctx* ctx, const float* r, int64_t W, float* l
     return NQMC_ERR_UNSUPPORTED;
   }
   const size_t smem = simple_smem_bytes(s, false);
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(simple_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
@@ -294,7 +295,8 @@ int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const doubl
     ctx->err = "SimpleWavefunction gradient: parameter block does not fit in shared memory";
     return NQMC_ERR_UNSUPPORTED;
   }
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
     NQMC_CUDA(cudaFuncSetAttribute(simple_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;

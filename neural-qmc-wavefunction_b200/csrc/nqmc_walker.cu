@@ -571,6 +571,47 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, const int it
   if (s == 123.456f) out[0] = s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// optimizer epilogue: optax.chain(clip_by_global_norm(c), adam(lr)) + apply_updates (optimizer/vmc.py:180-184,256-261)
+__global__ void __launch_bounds__(256) adam_norm_kernel(const double* __restrict__ gsum, const double* __restrict__ hdr,
+                                                        const int P, double* __restrict__ part) {
+  const double sc = 2.0 / fmax(hdr[NQMC_HDR_N], 1.0);
+  double a = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const double g = (double)(float)(sc * gsum[i]);        // the gradient is a float32 pytree in the reference
+    a += g * g;
+  }
+  __shared__ double sh[8];
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) adam_apply_kernel(const double* __restrict__ gsum, const double* __restrict__ hdr,
+                                                         const double* __restrict__ part, const int nblk, const int P,
+                                                         float* __restrict__ theta, float* __restrict__ m,
+                                                         float* __restrict__ v, const float lr, const float clip,
+                                                         const float bc1, const float bc2, double* __restrict__ norm_out) {
+  double n2 = 0;
+  for (int b = 0; b < nblk; ++b) n2 += part[b];            // every thread: same order => same value
+  const double norm = sqrt(n2);
+  if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+  const float scale = norm >= (double)clip ? (float)((double)clip / norm) : 1.0f;   // optax keeps g when ||g|| < max_norm
+  const double sc = 2.0 / fmax(hdr[NQMC_HDR_N], 1.0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const float g = (float)(sc * gsum[i]) * scale;
+    const float mi = 0.9f * m[i] + 0.1f * g;
+    const float vi = 0.999f * v[i] + 0.001f * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + 1e-8f);
+  }
+}
+
 template <typename F>
 int dispatch_ns(nqmc_ctx* ctx, F&& f) {
   const int ns = ctx->sys.n_up > ctx->sys.n_dn ? ctx->sys.n_up : ctx->sys.n_dn;
@@ -709,5 +750,19 @@ int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
+  return NQMC_OK;
+}
+
+int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,
+                 float clip, double* norm_out, cudaStream_t st) {
+  const int P = ctx->sys.P;
+  int nblk = (P + 255) / 256;
+  if (nblk > 128) nblk = 128;
+  adam_norm_kernel<<<nblk, 256, 0, st>>>(gsum, hdr, P, ctx->part_walk);
+  NQMC_LAUNCH_CHECK();
+  const float bc1 = 1.0f - powf(0.9f, (float)count), bc2 = 1.0f - powf(0.999f, (float)count);
+  adam_apply_kernel<<<(P + 255) / 256, 256, 0, st>>>(gsum, hdr, ctx->part_walk, nblk, P, ctx->theta, m, v, lr, clip, bc1, bc2,
+                                                     norm_out);
+  NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }

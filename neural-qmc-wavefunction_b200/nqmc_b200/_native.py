@@ -25,7 +25,7 @@ EXPORTS = [
     "nqmc_leaf_info", "nqmc_set_params", "nqmc_set_params_host", "nqmc_aos_to_soa", "nqmc_soa_to_aos",
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
-    "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores",
+    "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
 ]
 
 
@@ -84,6 +84,9 @@ def load_library():
     lib.nqmc_launch_count.restype = i64
     lib.nqmc_rng_fill.argtypes = [vp, u64, u64, i64, i64, vp, vp, vp]
     lib.nqmc_profile.argtypes = [vp, C.c_int]
+    lib.nqmc_get_params.argtypes = [vp, vp, i64, vp]
+    lib.nqmc_get_params_host.argtypes = [vp, vp, i64, vp]
+    lib.nqmc_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, vp, vp]
     lib.nqmc_use_tensor_cores.argtypes = [vp, C.c_int]
     lib.nqmc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.nqmc_ffma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp]
@@ -183,6 +186,17 @@ class Context:
             if tuple(th.shape) != (self.P,):
                 raise ValueError(f"theta must have shape ({self.P},)")
             self._check(self.lib.nqmc_set_params(self.h, th.data_ptr(), self.P, self.stream), "nqmc_set_params")
+
+    def get_params(self) -> np.ndarray:
+        th = np.empty(self.P, dtype=np.float32)
+        self._check(self.lib.nqmc_get_params_host(self.h, th.ctypes.data, self.P, self.stream), "nqmc_get_params_host")
+        return th
+
+    def adam_step(self, gsum, hdr, m, v, count: int, lr: float, clip: float, grad_norm=None):
+        """Fused clip + Adam on the device; theta inside the ctx is updated in place."""
+        self.reserve(max(self.cap, 1))
+        self._check(self.lib.nqmc_adam_step(self.h, gsum.data_ptr(), hdr.data_ptr(), m.data_ptr(), v.data_ptr(), int(count),
+                                            float(lr), float(clip), _ptr(grad_norm), self.stream), "nqmc_adam_step")
 
     # ------------------------------------------------------------------ layout
     def to_soa(self, r_aos):

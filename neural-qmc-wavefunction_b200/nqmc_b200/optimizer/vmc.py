@@ -99,6 +99,7 @@ class VMCOptimizer:
     n_burn: int = 200
     step_size: float = 0.5
     clip_grad: float = 1.0
+    device_update: bool = False     # extension: fused clip + Adam on the GPU, theta stays resident
 
     def _local_chains(self) -> Tuple[int, int]:
         rank, ws = parallel.world()
@@ -128,8 +129,11 @@ class VMCOptimizer:
         samples, sampler_state, acc = sampler.sample_device(
             key, log_prob_fn, state.sampler_state, n_samples=self.n_samples,
             n_burn=self.n_burn if state.step == 0 else 10, n_thin=1, walker_id0=lo)[:3]       # vmc.py:242-248
-        gradient, mean_energy, energy_std = compute_gradient(wavefunction, params, samples, molecule)
         rank, ws = parallel.world()
+        if self.device_update:
+            new_state, metrics = self._device_update(state, wavefunction, molecule, samples, sampler_state, acc, lo, hi)
+            return new_state, metrics
+        gradient, mean_energy, energy_std = compute_gradient(wavefunction, params, samples, molecule)
         if ws > 1:
             a = torch.tensor([acc * (hi - lo), float(hi - lo)], dtype=torch.float64,
                              device=samples.device if torch.distributed.get_backend() == "nccl" else "cpu")
@@ -142,6 +146,37 @@ class VMCOptimizer:
         new_state = VMCState(new_params, opt_state, sampler_state, state.step + 1)
         metrics = {"energy": float(mean_energy), "energy_std": float(energy_std), "acceptance_rate": float(acc),
                    "grad_norm": grad_norm}
+        return new_state, metrics
+
+    def _device_update(self, state, wavefunction, molecule, samples, sampler_state, acc, lo, hi):
+        """E_L, centred gradient sums, global-norm clip and Adam all on the device (nqmc_adam_step)."""
+        import torch
+        params = state.params
+        ctx, r, e, hdr = _energies_device(wavefunction, params, samples, molecule)
+        dev = ctx.dev()
+        gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
+        ctx.walker_step_b(r, e, hdr, gsum)
+        parallel.all_reduce_sum_(gsum)
+        opt = state.opt_state
+        mu = torch.as_tensor(opt["mu"]).to(dev, torch.float32).contiguous()
+        nu = torch.as_tensor(opt["nu"]).to(dev, torch.float32).contiguous()
+        gn = torch.zeros(1, dtype=torch.float64, device=dev)
+        count = int(opt["count"]) + 1
+        ctx.adam_step(gsum, hdr, mu, nu, count, self.learning_rate, self.clip_grad, grad_norm=gn)
+        new_params = unravel(ctx.get_params(), params)
+        h = hdr.cpu().numpy()
+        n = h[HDR_N]
+        mean = h[HDR_SUM_E] / n
+        var = max(h[HDR_SUM_E2] / n - mean * mean, 0.0)
+        rank, ws = parallel.world()
+        if ws > 1:
+            a = torch.tensor([acc * (hi - lo), float(hi - lo)], dtype=torch.float64,
+                             device=dev if torch.distributed.get_backend() == "nccl" else "cpu")
+            parallel.all_reduce_sum_(a)
+            acc = float(a[0] / a[1])
+        new_state = VMCState(new_params, {"count": count, "mu": mu, "nu": nu}, sampler_state, state.step + 1)
+        metrics = {"energy": float(mean), "energy_std": float(np.sqrt(var) / np.sqrt(n)), "acceptance_rate": float(acc),
+                   "grad_norm": float(gn.item())}
         return new_state, metrics
 
     def train(self, key, wavefunction, params: Params, molecule, n_steps: int, log_every: int = 10,

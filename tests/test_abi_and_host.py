@@ -146,3 +146,24 @@ def test_combine_gradient_equals_reference_estimator():
     gsum = ((e - e.mean())[:, None] * O).sum(0)
     g2, m2, s2 = parallel.combine_gradient(hdr, gsum)
     assert np.allclose(g2, g, rtol=1e-12) and np.isclose(m2, mean) and np.isclose(s2, std, rtol=1e-8)
+
+
+def test_checkpoint_roundtrip_host(tmp_path):
+    from nqmc_b200.checkpoint import load_checkpoint, save_checkpoint
+    from nqmc_b200.optimizer.vmc import VMCState
+    from nqmc_b200.sampler import SamplerState
+    mol = hydrogen_chain(4)
+    wf = AntisymmetricWavefunction(2, 2, (32, 32), use_cusp=True, use_backflow=True, molecule=mol)
+    params = wf.init(nqrandom.PRNGKey(1))
+    rng = np.random.default_rng(0)
+    n = P.ravel(params).size
+    opt = {"count": 7, "mu": rng.standard_normal(n).astype(np.float32), "nu": rng.random(n).astype(np.float32)}
+    ss = SamplerState(rng.standard_normal((16, 4, 3)).astype(np.float32), rng.standard_normal(16).astype(np.float32),
+                      rng.integers(0, 5, 16).astype(np.float32), 11)
+    st = VMCState(params, opt, ss, 7)
+    save_checkpoint(str(tmp_path / "c.npz"), st, energy=-2.01, key=nqrandom.PRNGKey(9))
+    st2, e, key = load_checkpoint(str(tmp_path / "c.npz"), wf.init(nqrandom.PRNGKey(2)))
+    assert e == -2.01 and st2.step == 7 and st2.opt_state["count"] == 7 and np.array_equal(key, nqrandom.PRNGKey(9))
+    assert np.array_equal(P.ravel(st2.params), P.ravel(params))
+    assert np.array_equal(st2.opt_state["mu"], opt["mu"]) and np.array_equal(st2.opt_state["nu"], opt["nu"])
+    assert np.array_equal(st2.sampler_state.positions, ss.positions) and st2.sampler_state.n_steps == 11

@@ -107,3 +107,50 @@ def test_reference_facing_signatures():
     assert abs(smp.get_acceptance_rate(st2) - rate) < 1e-6
     with pytest.raises(TypeError):
         smp.step(nqmc.random.PRNGKey(8), st, lambda x: 0.0)
+
+
+def test_device_adam_matches_host_update_and_checkpoint_roundtrip(tmp_path):
+    """the fused device clip+Adam gives the host (optax-formula) trajectory; a checkpoint
+    written mid-run resumes to the same numbers."""
+    import nqmc_b200 as nqmc
+    from nqmc_b200.checkpoint import load_checkpoint, save_checkpoint
+    from nqmc_b200.optimizer import VMCOptimizer
+    from nqmc_b200.params import ravel
+    from nqmc_b200.systems.molecule import hydrogen_chain
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction
+    mol = hydrogen_chain(4, 1.8)
+    wf = AntisymmetricWavefunction(2, 2, (64, 64), use_cusp=True, molecule=mol)
+    p0 = wf.init(nqmc.random.PRNGKey(0))
+    runs = {}
+    for dev_upd in (False, True):
+        opt = VMCOptimizer(learning_rate=1e-3, n_samples=4, n_chains=512, n_burn=20, step_size=0.5, clip_grad=1.0, device_update=dev_upd)
+        key = nqmc.random.PRNGKey(7)
+        key, k0 = nqmc.random.split(key)
+        st = opt.init(k0, wf, p0, mol)
+        hist = []
+        for i in range(6):
+            key, ks = nqmc.random.split(key)
+            st, m = opt.step(ks, st, wf, mol)
+            hist.append(m)
+            if i == 2 and not dev_upd:
+                save_checkpoint(str(tmp_path / "ck"), st, energy=m["energy"], key=key)
+        runs[dev_upd] = (st, hist)
+    th_h, th_d = ravel(runs[False][0].params), ravel(runs[True][0].params)
+    # trajectories share RNG streams but decorrelate slowly (an MH decision flips when theta moves by 1e-7), so the
+    # first step is compared tightly and the end point loosely
+    a, b = runs[False][1][0], runs[True][1][0]
+    assert abs(a["energy"] - b["energy"]) < 1e-4 * max(1, abs(a["energy"]))
+    assert abs(a["grad_norm"] - b["grad_norm"]) < 2e-2 * max(1, a["grad_norm"])
+    assert abs(a["energy_std"] - b["energy_std"]) < 1e-3 * a["energy_std"] + 1e-6
+    assert np.max(np.abs(th_h - th_d)) < 2e-3, np.max(np.abs(th_h - th_d))          # 6 Adam steps of size 1e-3
+    assert np.median(np.abs(th_h - th_d)) < 2e-5
+    # resume from the checkpoint taken after step 3 and replay steps 4..6 with the same keys
+    st_r, e_r, key_r = load_checkpoint(str(tmp_path / "ck"), p0)
+    assert st_r.step == 3 and st_r.opt_state["count"] == 3 and np.isfinite(e_r)
+    opt = VMCOptimizer(learning_rate=1e-3, n_samples=4, n_chains=512, n_burn=20, step_size=0.5, clip_grad=1.0)
+    key = key_r
+    for i in range(3):
+        key, ks = nqmc.random.split(key)
+        st_r, m = opt.step(ks, st_r, wf, mol)
+    assert np.allclose(ravel(st_r.params), th_h, rtol=0, atol=1e-6)
+    assert np.array_equal(st_r.sampler_state.positions, runs[False][0].sampler_state.positions)
