@@ -84,13 +84,14 @@ int check_w(nqmc_ctx* ctx, int64_t W) {
 void free_scratch(nqmc_ctx* c) {
   void* ptrs[] = {c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
-                  c->part_mlp, c->hdr_tmp};
+                  c->part_mlp, c->hdr_tmp, c->jas_sums};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   c->x_cur = c->x_prop = c->vvec = nullptr;
   c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
-  c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = nullptr;
+  c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
+  c->jas_valid_for = nullptr;
   c->part_mlp = nullptr;
   c->cap_w = 0;
 }
@@ -241,6 +242,7 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   NQMC_CUDA(cudaMalloc(&ctx->nacc_stage, w * f));
   NQMC_CUDA(cudaMalloc(&ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double)));
   NQMC_CUDA(cudaMalloc(&ctx->hdr_tmp, NQMC_HDR_SIZE * sizeof(double)));
+  NQMC_CUDA(cudaMalloc(&ctx->jas_sums, 8 * sizeof(double)));
   NQMC_CUDA(cudaMalloc(&ctx->gsum_stage, (size_t)s.P * sizeof(double)));
   ctx->n_blk_walk = 65536;
   NQMC_CUDA(cudaMalloc(&ctx->part_walk, (size_t)ctx->n_blk_walk * 16 * sizeof(double)));
@@ -389,6 +391,7 @@ int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, con
 }
 
 static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
+  ctx->jas_valid_for = nullptr;
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
   if (ctx->sys.use_bf) {
     int rc = nq_launch_backflow_x(ctx, r, W, ctx->x_cur, st);
@@ -417,7 +420,11 @@ static int grads_core(nqmc_ctx* ctx, const float* r, const float* wgt, const dou
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_grads(ctx, r, wgt, hdr, e_l, W, out, st);
   int rc = nq_launch_orb_bwd(ctx, ctx->sys.use_bf ? ctx->x_cur : r, wgt, hdr, e_l, W, out, st);
   if (rc) return rc;
-  rc = nq_launch_walker_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  if (wgt == nullptr && hdr != nullptr && e_l != nullptr && ctx->jas_valid_for == e_l)
+    rc = nq_launch_jastrow_from_sums(ctx, hdr, out, st);      // sums were taken by the fused phase-A kernel
+  else
+    rc = nq_launch_walker_grads(ctx, r, wgt, hdr, e_l, W, out, st);
+  ctx->jas_valid_for = nullptr;
   if (rc) return rc;
   if (ctx->sys.use_bf) rc = nq_launch_bf_grads(ctx, r, wgt, hdr, e_l, W, out, st);
   return rc;
@@ -457,6 +464,17 @@ int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normal
   NQMC_CUDA(cudaSetDevice(ctx->device));
   rc = mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, nullptr, n_acc, S(st));
   if (rc) return rc;
+  ctx->jas_valid_for = nullptr;
+  if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC && !ctx->sys.use_cusp && !ctx->sys.use_bf &&
+      (W + 127) / 128 <= ctx->n_blk_walk) {
+    // fused: orbital pass, then E_L assembly + header + Jastrow-scalar sums in one kernel
+    rc = nq_launch_orb_eval(ctx, r, W, 5, ctx->phi, S(st));
+    if (rc) return rc;
+    rc = nq_launch_assemble_stats(ctx, r, W, e_l, ctx->wgt, hdr, S(st));
+    if (rc) return rc;
+    ctx->jas_valid_for = e_l;
+    return NQMC_OK;
+  }
   rc = energy_core(ctx, r, W, e_l, nullptr, S(st));
   if (rc) return rc;
   return nq_launch_stats(ctx, e_l, ctx->wgt, W, hdr, S(st));

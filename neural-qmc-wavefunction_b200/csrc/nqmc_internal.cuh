@@ -87,6 +87,8 @@ struct nqmc_ctx {
   int n_cta_bwd = 0;
   int p_mlp = 0;               // scalars in one orbital network
   double* hdr_tmp = nullptr;   // [8]
+  double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
+  const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
   // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
   bool prof_on = false;
   static constexpr int PROF_KINDS = 6, PROF_RING = 512;
@@ -206,3 +208,6 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
 int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
 int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,
                  float clip, double* norm_out, cudaStream_t st);
+int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,
+                             cudaStream_t st);
+int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st);

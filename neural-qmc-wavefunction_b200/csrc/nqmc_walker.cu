@@ -273,6 +273,92 @@ __global__ void __launch_bounds__(WT) assemble_kernel(const DevSys s, const floa
   if (sign_out) sign_out[w] = sg;
 }
 
+// Fused variant for the walker step (no cusp / backflow): E_L assembly + per-block partial sums of the energy
+// header AND of the four Jastrow-scalar log-derivatives (sum O, sum E*O), so that neither the statistics pass nor
+// the separate per-walker gradient kernel has to re-read the walkers:  sum_w (E_w - Ebar) O_w = sum E O - Ebar sum O.
+// part[blk][16] = n, sum E, sum E^2, n_accept, n_bad, sum O[4] (a_ee, a_en, b_ee, b_en), sum E O[4]
+template <int NS>
+__global__ void __launch_bounds__(WT) assemble_stats_kernel(const DevSys s, const float* __restrict__ theta,
+                                                            const float* __restrict__ r, const float* __restrict__ phi,
+                                                            float* __restrict__ inv_out, const int64_t W,
+                                                            float* __restrict__ e_l, const float* __restrict__ acc_flag,
+                                                            double* __restrict__ part) {
+  const int64_t w = (int64_t)blockIdx.x * WT + threadIdx.x;
+  const bool valid = w < W;
+  double acc[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+  if (valid) {
+    float la, sg, T, ven, vee;
+    walker_eval<NS, true>(s, theta, r, phi, inv_out, W, w, la, sg, T, ven, vee);
+    const float e = T + ven + vee + s.v_nn;            // molecular.py:175
+    e_l[w] = e;
+    if (acc_flag) acc[3] = acc_flag[w];
+    if (isfinite(e)) {
+      acc[0] = 1.0; acc[1] = e; acc[2] = (double)e * e;
+      const float a_ee = theta[s.jas_a_ee], b_ee = theta[s.jas_b_ee];
+      const float a_en = theta[s.jas_a_en], b_en = theta[s.jas_b_en];
+      float g_aee = 0.f, g_bee = 0.f, g_aen = 0.f, g_ben = 0.f;
+      for (int i = 0; i < s.N; ++i) {
+        const float xi = r[(int64_t)(3 * i) * W + w], yi = r[(int64_t)(3 * i + 1) * W + w], zi = r[(int64_t)(3 * i + 2) * W + w];
+        for (int j = i + 1; j < s.N; ++j) {
+          const float dx = xi - r[(int64_t)(3 * j) * W + w], dy = yi - r[(int64_t)(3 * j + 1) * W + w], dz = zi - r[(int64_t)(3 * j + 2) * W + w];
+          const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float q = 1.0f / fmaf(b_ee, d, 1.0f);
+          g_aee = fmaf(d, q, g_aee);
+          g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
+        }
+        for (int a = 0; a < s.A; ++a) {
+          const float dx = xi - s.R[3 * a], dy = yi - s.R[3 * a + 1], dz = zi - s.R[3 * a + 2];
+          const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float q = 1.0f / fmaf(b_en, d, 1.0f);
+          g_aen = fmaf(d, q, g_aen);
+          g_ben = fmaf(-a_en * d * d, q * q, g_ben);
+        }
+      }
+      acc[5] = g_aee; acc[6] = g_aen; acc[7] = g_bee; acc[8] = g_ben;
+      acc[9] = (double)e * g_aee; acc[10] = (double)e * g_aen; acc[11] = (double)e * g_bee; acc[12] = (double)e * g_ben;
+    } else {
+      acc[4] = 1.0;
+    }
+  }
+  __shared__ double sh[WT / 32][13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    const double t = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 13) {
+    double t = 0;
+    for (int q = 0; q < WT / 32; ++q) t += sh[q][threadIdx.x];
+    part[(int64_t)blockIdx.x * NPART + threadIdx.x] = t;
+  }
+}
+// hdr[0..4] and jas[0..7] from the block partials (one warp per slot, fixed order => deterministic)
+__global__ void stats13_finish_kernel(const double* __restrict__ part, const int nblk, double* __restrict__ hdr,
+                                      double* __restrict__ jas) {
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0;
+  if (slot < 13)
+    for (int b = lane; b < nblk; b += 32) a += part[(int64_t)b * NPART + slot];
+  a = warp_sum(a);
+  if (lane == 0) {
+    if (slot < 5) hdr[slot] = a;
+    else if (slot < 13) jas[slot - 5] = a;
+    else if (slot < 16) hdr[slot - 8] = 0.0;          // hdr[5..7]
+  }
+}
+// out[jastrow scalar] = sum E O - Ebar sum O   with Ebar from the (all-reduced) header
+__global__ void jastrow_from_sums_kernel(const DevSys s, const double* __restrict__ jas, const double* __restrict__ hdr,
+                                         double* __restrict__ out) {
+  const int q = threadIdx.x;
+  if (q >= 4) return;
+  const double ebar = hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0);
+  const int o = q == 0 ? s.jas_a_ee : (q == 1 ? s.jas_a_en : (q == 2 ? s.jas_b_ee : s.jas_b_en));
+  out[o] = jas[4 + q] - ebar * jas[q];
+}
+
 // ---------------------------------------------------------------------------------------------
 // proposal: r' = r + sigma * n   (metropolis.py:119-121)
 __global__ void propose_kernel(const DevSys s, const float* __restrict__ r, const float* __restrict__ normals,
@@ -763,6 +849,34 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
   const float bc1 = 1.0f - powf(0.9f, (float)count), bc2 = 1.0f - powf(0.999f, (float)count);
   adam_apply_kernel<<<(P + 255) / 256, 256, 0, st>>>(gsum, hdr, ctx->part_walk, nblk, P, ctx->theta, m, v, lr, clip, bc1, bc2,
                                                      norm_out);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
+// E_L assembly fused with the energy header and the Jastrow-scalar sums (walker step without cusp / backflow)
+int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,
+                             cudaStream_t st) {
+  const int nblk = (int)((W + WT - 1) / WT);
+  if (nblk > ctx->n_blk_walk) {
+    ctx->err = "assemble_stats: too many walkers for the partial buffer";
+    return NQMC_ERR_STATE;
+  }
+  int rc = dispatch_ns(ctx, [&](auto ns) -> int {
+    constexpr int NS = decltype(ns)::value;
+    ProfScope ps(ctx, NQ_PROF_ASSEMBLE, st);
+    assemble_stats_kernel<NS><<<nblk, WT, 0, st>>>(ctx->sys, ctx->theta, r, ctx->phi, ctx->inv, W, e_l, acc_flag,
+                                                   ctx->part_walk);
+    NQMC_LAUNCH_CHECK();
+    return (int)NQMC_OK;
+  });
+  if (rc) return rc;
+  stats13_finish_kernel<<<1, 32 * 16, 0, st>>>(ctx->part_walk, nblk, hdr, ctx->jas_sums);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
+int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st) {
+  jastrow_from_sums_kernel<<<1, 32, 0, st>>>(ctx->sys, ctx->jas_sums, hdr, out);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
