@@ -60,7 +60,10 @@ def local_energy_batched(wavefunction, params, r_batch, molecule):
     """E_L for a batch (B,N,3) -> (B,) (molecular.py:178-197)."""
     if not isinstance(wavefunction, Wavefunction):
         raise TypeError("local_energy needs a native nqmc_b200 Wavefunction")
+    r_batch = np.asarray(r_batch, dtype=np.float32)
+    if r_batch.shape[0] == 0:                               # empty batch: vmap over nothing
+        return np.zeros((0,), dtype=np.float32)
     ctx = wavefunction.context(molecule)
     ctx.set_params(ravel(params))
-    soa = ctx.to_soa(np.asarray(r_batch, dtype=np.float32))
+    soa = ctx.to_soa(r_batch)
     return ctx.local_energy(soa).cpu().numpy()

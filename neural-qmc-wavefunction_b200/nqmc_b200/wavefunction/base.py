@@ -63,6 +63,8 @@ class Wavefunction(ABC):
         ctx.set_params(ravel(params))
         r = np.asarray(r, dtype=np.float32)
         single = r.ndim == 2
+        if not single and r.shape[0] == 0:                  # empty batch
+            return np.zeros((0,), np.float32), np.zeros((0,), np.float32)
         soa = ctx.to_soa(r[None] if single else r)
         sg, la = ctx.log_psi(soa)
         sg, la = sg.cpu().numpy(), la.cpu().numpy()

@@ -216,3 +216,74 @@ def test_device_rng_matches_philox_oracle(case):
     assert np.array_equal(u.cpu().numpy(), u_ref), "uniform stream must be bit-identical"
     got = n.cpu().numpy().T.reshape(W, ctx.n_elec, 3)
     assert np.max(np.abs(got - n_ref)) <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# edge cases (empty / single / ragged batches, one-electron systems, node hits)
+def test_h_atom_exact_energy_on_device():
+    """K-1 on the device: psi = exp(-r) (SimpleWavefunction, zero MLP, alpha = 1, one nucleus) => E_L = -0.5 pointwise;
+    and the antisymmetric ansatz with n_up = 1, n_dn = 0 (an empty spin-down determinant) against the oracle."""
+    from oracle.layout import OracleNet, hydrogen_chain_system, init_theta, param_count
+    s = hydrogen_chain_system(1)
+    net = OracleNet(kind=KIND_SIMPLE, hidden=(8, 8))
+    ctx = make_context(s, net)
+    ctx.set_params(np.zeros(param_count(s, net), np.float32))
+    r = np.random.default_rng(0).standard_normal((77, 1, 3)).astype(np.float32)
+    e = ctx.local_energy(ctx.to_soa(r)).cpu().numpy()
+    assert np.max(np.abs(e + 0.5)) < 2e-5
+    _, la = ctx.log_psi(ctx.to_soa(r))
+    assert np.allclose(la.cpu().numpy(), -np.linalg.norm(r[:, 0], axis=-1), atol=1e-6)
+    net1 = OracleNet(hidden=(32, 32))
+    th = init_theta(s, net1, 4).astype(np.float32)
+    c1 = make_context(s, net1)
+    c1.set_params(th)
+    o = make_oracle(s, net1)
+    e1 = c1.local_energy(c1.to_soa(r)).cpu().numpy()
+    e_ref, _, _, _ = o.local_energy(th.astype(np.float64), r.astype(np.float64))
+    assert np.median(rel_err(e1, e_ref)) < 1e-5
+    g = c1.grad_accum(c1.to_soa(r), None).cpu().numpy()
+    O = o.grad_log_psi(th.astype(np.float64), r.astype(np.float64))
+    assert np.median(np.abs(g - O.sum(0)) / np.maximum(np.abs(O).sum(0), 1e-3)) < 1e-5
+
+
+def test_single_walker_and_empty_batch():
+    import nqmc_b200 as nqmc
+    from nqmc_b200.hamiltonian import local_energy_batched
+    from nqmc_b200.systems.molecule import hydrogen_chain
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction
+    mol = hydrogen_chain(4)
+    wf = AntisymmetricWavefunction(2, 2, (64, 64), molecule=mol)
+    p = wf.init(nqmc.random.PRNGKey(1))
+    r = (mol.positions[np.arange(4) % 4] + 0.3).astype(np.float32)
+    one = local_energy_batched(wf, p, r[None], mol)
+    many = local_energy_batched(wf, p, np.repeat(r[None], 300, axis=0), mol)
+    assert one.shape == (1,) and np.all(many == one[0])               # a walker's result does not depend on the batch
+    assert local_energy_batched(wf, p, np.zeros((0, 4, 3), np.float32), mol).shape == (0,)
+    assert wf(p, np.zeros((0, 4, 3), np.float32)).shape == (0,)
+
+
+def test_node_hit_is_counted_not_propagated():
+    """A walker sitting exactly on a nucleus has a non-finite E_L: it is counted in hdr[N_BAD], excluded from the sums,
+    and the gradient stays finite (the reference would turn the whole batch mean into NaN)."""
+    import torch
+    s, net, theta, r = make_case(n_atoms=4, hidden=64, W=256, burn=5)
+    r = r.copy()
+    r[17, 0] = s.R[0].astype(np.float32)
+    ctx = make_context(s, net)
+    ctx.set_params(theta)
+    dev = ctx.dev()
+    soa = ctx.to_soa(r)
+    _, la = ctx.log_psi(soa)
+    logp = (2 * la).contiguous()
+    e_l = torch.empty(256, dtype=torch.float32, device=dev)
+    hdr = torch.empty(8, dtype=torch.float64, device=dev)
+    gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
+    u = torch.ones(256, device=dev)                                   # log(1) = 0 >= any negative ratio...
+    n0 = torch.zeros((12, 256), device=dev)                           # ...and zero displacement: nothing moves
+    ctx.walker_step(soa, logp, 0.3, e_l, hdr, gsum, normals=n0, uniforms=u)
+    h = hdr.cpu().numpy()
+    e = e_l.cpu().numpy()
+    assert not np.isfinite(e[17]) and np.isfinite(np.delete(e, 17)).all()
+    assert h[4] == 1 and h[0] == 255
+    assert abs(h[1] - np.delete(e, 17).astype(np.float64).sum()) < 1e-6 * np.abs(np.delete(e, 17)).sum()
+    assert np.isfinite(gsum.cpu().numpy()).all()
