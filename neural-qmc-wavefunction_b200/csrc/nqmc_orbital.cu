@@ -15,6 +15,8 @@
 // feeds 4 rows, weights as Wp[k][4*cg+jj] so one LDS.128 feeds 4 columns.  Column ownership is
 // interleaved (thread cg owns columns cg, cg+CG, cg+2CG, cg+3CG) and the k-slice stride is
 // C*TR+4 floats, which makes the epilogue's STS.128 of freshly activated columns bank-conflict free.
+#include <cstdlib>
+
 #include "nqmc_internal.cuh"
 
 namespace {
@@ -757,7 +759,9 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
     if (H == 128) return launch_eval_t<128, 1, 8, 256>(ctx, r, W, phi, st);
   } else if (channels == 5) {
     if (ctx->use_tc) {
-      int rc = nq_launch_orb_eval5_tc(ctx, r, W, phi, st);
+      static const bool lap2 = []() { const char* e = getenv("NQMC_LAP_TC"); return e == nullptr || atoi(e) != 0; }();
+      int rc = lap2 ? nq_launch_orb_lap_tc(ctx, r, W, phi, st) : NQMC_ERR_UNSUPPORTED;   // A operand in TMEM
+      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_eval5_tc(ctx, r, W, phi, st);   // A operand in shared memory
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
     if (H == 32) return launch_eval_t<32, 5, 4, 256>(ctx, r, W, phi, st);
