@@ -212,3 +212,4 @@ int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_
                              cudaStream_t st);
 int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st);
 int nq_launch_orb_lap_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
+int nq_launch_orb_lap_pc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
