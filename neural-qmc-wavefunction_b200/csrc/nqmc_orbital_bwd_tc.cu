@@ -33,33 +33,41 @@ constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G2 = 128, C_G1 = 192, C_AH = 256, C_AL = 320;
-constexpr int RGH = (H + 1) * 16;     // row-group stride of the transposed h1 buffer: 64 units + the ones unit = 1040 B
-constexpr int RGD = H * 16;           // row-group stride of the transposed delta buffer                          = 1024 B
+// Row-group strides of the transposed buffers.  A quarter warp (rows 4g..4g+7, 8 lanes x 16 B) stores to two
+// consecutive row groups, so the stride has to be 64 (mod 128) bytes for the two halves to land in disjoint banks.
+constexpr int RGH_MIN = (H + 1) * 16; // 64 units + the ones unit = 1040 B (unpadded: 2-way store conflicts)
+constexpr int RG_PAD = (H + 4) * 16;  // 1088 B = 64 (mod 128)
+constexpr int FS_LD = 128 + 4;        // leading dimension of the [feature][row] staging array (float4 reads, stride 4 banks)
+constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NRG = ROWS / 4;         // 32 row groups (granule = 4 consecutive rows of one unit)
 constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                                                   = 16384 B
 
 struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
   int hT_hi, hT_lo, dT_hi, dT_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
   int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the feature buffer
+  int rgh, rgd;       // row-group strides of the transposed h1 / delta buffers
 };
-__host__ __device__ inline SmemMap make_map(int F) {
+__host__ __device__ inline SmemMap make_map(int F, bool pad_h = true) {
   SmemMap m;
   m.n_fu = 4 * ((F + 1 + 3) / 4);
   m.rgf = m.n_fu * 16;
+  m.rgd = RG_PAD;
+  m.rgh = pad_h ? RG_PAD : RGH_MIN;
   int o = 0;
   m.fT_hi = o; o += NRG * m.rgf;
   m.fT_lo = o; o += NRG * m.rgf;
-  m.hT_hi = o; o += NRG * RGH;
-  m.hT_lo = o; o += NRG * RGH;
-  m.dT_hi = o; o += NRG * RGD;
-  m.dT_lo = o; o += NRG * RGD;
+  m.hT_hi = o; o += NRG * m.rgh;
+  m.hT_lo = o; o += NRG * m.rgh;
+  m.dT_hi = o; o += NRG * m.rgd;
+  m.dT_lo = o; o += NRG * m.rgd;
   m.wa_hi = o; o += WB;
   m.wa_lo = o; o += WB;
   m.wb_hi = o; o += WB;
   m.wb_lo = o; o += WB;
-  m.fstage = o; o += m.n_fu * ROWS * 4;
+  m.fstage = o; o += m.n_fu * FS_LD * 4;
   m.misc = o; o += (F * H + 3 * H + H + 8) * 4 + 64;
   m.total = o;
+  if (pad_h && m.total > SMEM_LIMIT) return make_map(F, false);   // many nuclei: give up the h1 padding to fit
   return m;
 }
 
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(TCT, 1)
 
   // ---- setup ----------------------------------------------------------------------------------------------
   for (int idx = tid; idx < mp.wa_hi / 16; idx += TCT) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int idx = tid; idx < mp.n_fu * ROWS; idx += TCT) fstage[idx] = 0.f;
+  for (int idx = tid; idx < mp.n_fu * FS_LD; idx += TCT) fstage[idx] = 0.f;
   for (int idx = tid; idx < F * H; idx += TCT) W1s[idx] = theta[off.W1 + idx];
   for (int q = tid; q < H; q += TCT) {
     b1s[q] = theta[off.b1 + q];
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   __syncthreads();
   // the ones unit (index 64) of the transposed h1 buffer -> row 64 of G2 = db2 ; hi = 1, lo stays 0
-  for (int g = tid; g < NRG; g += TCT) *reinterpret_cast<float4*>(smem + mp.hT_hi + g * RGH + H * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int g = tid; g < NRG; g += TCT) *reinterpret_cast<float4*>(smem + mp.hT_hi + g * mp.rgh + H * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
   if (tid == 0) {
     for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,33 +263,42 @@ __global__ void __launch_bounds__(TCT, 1)
   const int c0 = UPT * quarter;                     // first hidden unit / output column of this thread
   const int t4 = tid & 3;                           // position inside the lane quad == row % 4
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  uint8_t* hT_hi = smem + mp.hT_hi + (row >> 2) * RGH;
-  uint8_t* hT_lo = smem + mp.hT_lo + (row >> 2) * RGH;
-  uint8_t* dT_hi = smem + mp.dT_hi + (row >> 2) * RGD;
-  uint8_t* dT_lo = smem + mp.dT_lo + (row >> 2) * RGD;
+  uint8_t* hT_hi = smem + mp.hT_hi + (row >> 2) * mp.rgh;
+  uint8_t* hT_lo = smem + mp.hT_lo + (row >> 2) * mp.rgh;
+  uint8_t* dT_hi = smem + mp.dT_hi + (row >> 2) * mp.rgd;
+  uint8_t* dT_lo = smem + mp.dT_lo + (row >> 2) * mp.rgd;
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
   bool first_tile = true;
-  for (int64_t item = chunk; item < n_items; item += n_chunks) {
+  // positions and reverse seed of one tile row; the next tile's are fetched while the current one computes
+  float nx = 0.f, ny = 0.f, nz = 0.f, nseed = 0.f;
+  auto fetch = [&](const int64_t item) {
     const int i = (int)(item % ns);
-    const int64_t w0 = (item / ns) * ROWS;
+    int64_t w = (item / ns) * ROWS + row;
+    const bool valid = w < W;
+    if (!valid) w = W - 1;
+    const int e = elec0 + i;
+    nx = r[(int64_t)(3 * e + 0) * W + w];
+    ny = r[(int64_t)(3 * e + 1) * W + w];
+    nz = r[(int64_t)(3 * e + 2) * W + w];
+    float wt = 1.0f;
+    if (wgt != nullptr) wt = wgt[w];
+    else if (e_l != nullptr) {
+      const float ev = e_l[w];
+      wt = isfinite(ev) ? ev - centerf : 0.f;
+    }
+    nseed = wt * inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
+    if (!valid || !isfinite(nseed)) nseed = 0.f;
+  };
+  if (worker && chunk < n_items) fetch(chunk);
+  for (int64_t item = chunk; item < n_items; item += n_chunks) {
     float h1[UPT], d2[UPT], seed = 0.f;
     if (worker) {
       // ---- positions, seed, features, layer 1 (FP32 FFMA) --------------------------------------------------
-      int64_t w = w0 + row;
-      const bool valid = w < W;
-      if (!valid) w = W - 1;
-      const int e = elec0 + i;
-      const float x = r[(int64_t)(3 * e + 0) * W + w], y = r[(int64_t)(3 * e + 1) * W + w], z = r[(int64_t)(3 * e + 2) * W + w];
-      float wt = 1.0f;
-      if (wgt != nullptr) wt = wgt[w];
-      else if (e_l != nullptr) {
-        const float ev = e_l[w];
-        wt = isfinite(ev) ? ev - centerf : 0.f;
-      }
-      seed = wt * inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
-      if (!valid || !isfinite(seed)) seed = 0.f;
+      const float x = nx, y = ny, z = nz;
+      seed = nseed;
+      if (item + n_chunks < n_items) fetch(item + n_chunks);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
       const float pc[3] = {x, y, z};
@@ -297,18 +314,18 @@ __global__ void __launch_bounds__(TCT, 1)
         }
       }
       if (quarter == 0) {
-        fstage[0 * ROWS + row] = x;
-        fstage[1 * ROWS + row] = y;
-        fstage[2 * ROWS + row] = z;
-        fstage[F * ROWS + row] = 1.0f;                  // ones unit -> db1
+        fstage[0 * FS_LD + row] = x;
+        fstage[1 * FS_LD + row] = y;
+        fstage[2 * FS_LD + row] = z;
+        fstage[F * FS_LD + row] = 1.0f;                  // ones unit -> db1
       }
       for (int a = 0; a < A; ++a) {
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
         const float ex = __expf(-dd);
         if (quarter == 0) {
-          fstage[(3 + a) * ROWS + row] = dd;
-          fstage[(3 + A + a) * ROWS + row] = ex;
+          fstage[(3 + a) * FS_LD + row] = dd;
+          fstage[(3 + A + a) * FS_LD + row] = ex;
         }
 #pragma unroll
         for (int v = 0; v < UPT / 4; ++v) {
@@ -349,8 +366,8 @@ __global__ void __launch_bounds__(TCT, 1)
       stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);                    // its G2 (reader of this buffer) was waited for already
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
       for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
-        const int f = idx / NRG, g = idx % NRG;
-        const float4 fv = *reinterpret_cast<const float4*>(fstage + f * ROWS + 4 * g);
+        const int g = idx / mp.n_fu, f = idx % mp.n_fu;     // consecutive lanes: consecutive 16-byte granules
+        const float4 fv = *reinterpret_cast<const float4*>(fstage + f * FS_LD + 4 * g);
         float4 h4, l4;
         split_tf32(fv.x, h4.x, l4.x);
         split_tf32(fv.y, h4.y, l4.y);
@@ -405,11 +422,11 @@ __global__ void __launch_bounds__(TCT, 1)
     if (warp == TCW / 32) {
       const uint32_t leader = elect_one();
       {
-        const uint64_t ah = umma_desc(sbase + mp.hT_hi, RGH, 128), al = umma_desc(sbase + mp.hT_lo, RGH, 128);
-        const uint64_t bh = umma_desc(sbase + mp.dT_hi, RGD, 128), bl = umma_desc(sbase + mp.dT_lo, RGD, 128);
+        const uint64_t ah = umma_desc(sbase + mp.hT_hi, mp.rgh, 128), al = umma_desc(sbase + mp.hT_lo, mp.rgh, 128);
+        const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
 #pragma unroll
         for (int ks = 0; ks < ROWS / 8; ++ks) {
-          const uint64_t ao = (uint64_t)((ks * 2 * RGH) >> 4), bo = (uint64_t)((ks * 2 * RGD) >> 4);
+          const uint64_t ao = (uint64_t)((ks * 2 * mp.rgh) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
           const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
           umma_ss(tmem_base + C_G2, ah + ao, bh + bo, acc, leader);
           umma_ss(tmem_base + C_G2, al + ao, bh + bo, 1u, leader);
@@ -440,10 +457,10 @@ __global__ void __launch_bounds__(TCT, 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       const uint64_t ah = umma_desc(sbase + mp.fT_hi, mp.rgf, 128), al = umma_desc(sbase + mp.fT_lo, mp.rgf, 128);
-      const uint64_t bh = umma_desc(sbase + mp.dT_hi, RGD, 128), bl = umma_desc(sbase + mp.dT_lo, RGD, 128);
+      const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
 #pragma unroll
       for (int ks = 0; ks < ROWS / 8; ++ks) {
-        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgf) >> 4), bo = (uint64_t)((ks * 2 * RGD) >> 4);
+        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgf) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
         const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
         umma_ss(tmem_base + C_G1, ah + ao, bh + bo, acc, leader);
         umma_ss(tmem_base + C_G1, al + ao, bh + bo, 1u, leader);
@@ -510,7 +527,7 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   const DevSys& s = ctx->sys;
   if (s.H != H) return NQMC_ERR_UNSUPPORTED;
   const SmemMap mp = make_map(s.F);
-  if (mp.total > 227 * 1024 || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
+  if (mp.total > SMEM_LIMIT || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
   if (const char* e = getenv("NQMC_TC_BWD"))
     if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
   static bool configured_dev[64] = {};
