@@ -190,13 +190,21 @@ __global__ void __launch_bounds__(TCT, 1)
     // =============================== worker warps ========================================================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t g = 0, t = 0;
+    float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
+    auto fetch = [&](const int64_t item) {
+      int64_t w = (item / ns) * ROWS + row;
+      if (w >= W) w = W - 1;
+      const int e = elec0 + (int)(item % ns);
+      nx = r[(int64_t)(3 * e + 0) * W + w];
+      ny = r[(int64_t)(3 * e + 1) * W + w];
+      nz = r[(int64_t)(3 * e + 2) * W + w];
+    };
+    if (chunk < n_items) fetch(chunk);
     for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
       const int i = (int)(item % ns);
       const int64_t w0 = (item / ns) * ROWS;
-      int64_t w = w0 + row;
-      if (w >= W) w = W - 1;
-      const int e = elec0 + i;
-      const float x = r[(int64_t)(3 * e + 0) * W + w], y = r[(int64_t)(3 * e + 1) * W + w], z = r[(int64_t)(3 * e + 2) * W + w];
+      const float x = nx, y = ny, z = nz;
+      if (item + n_chunks < n_items) fetch(item + n_chunks);
       // features of this row with gradient / Laplacian, in registers for all 8 chunks
       float fd[NA][CH], fe[NA][CH];
 #pragma unroll
