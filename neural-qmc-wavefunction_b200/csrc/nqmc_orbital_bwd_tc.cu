@@ -45,11 +45,13 @@ constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                 
 struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
   int hT_hi, hT_lo, dT_hi, dT_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
   int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the feature buffer
+  int n_g1;
   int rgh, rgd;       // row-group strides of the transposed h1 / delta buffers
 };
 __host__ __device__ inline SmemMap make_map(int F, bool pad_h = true) {
   SmemMap m;
   m.n_fu = 4 * ((F + 1 + 3) / 4);
+  m.n_g1 = 8 * ((F + 1 + 7) / 8);   // N of the G1^T MMAs (a multiple of 8): columns >= n_fu read into the next row group, ignored
   m.rgf = m.n_fu * 16;
   m.rgd = RG_PAD;
   m.rgh = pad_h ? RG_PAD : RGH_MIN;
@@ -81,11 +83,12 @@ constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >>
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // A and B from shared memory
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t leader) {
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                        uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred p, l;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 l, %5, 0;\n\t"
       "@l tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(leader)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 // A from tensor memory, B from shared memory
@@ -127,6 +130,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -182,13 +194,15 @@ __device__ __forceinline__ void stage_cols_smem(uint8_t* hi_rg, uint8_t* lo_rg, 
   }
 }
 
+// NA = number of nuclei when > 0 (feature loops fully unrolled), 0 = run-time count
+template <int NA>
 __global__ void __launch_bounds__(TCT, 1)
     orb_bwd_tc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r,
                       const float* __restrict__ inv, const float* __restrict__ wgt, const double* __restrict__ hdr,
                       const float* __restrict__ e_l, const int64_t W, float* __restrict__ part, const int n_chunks,
                       const int p_mlp) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int F = s.F, A = s.A;
+  const int A = NA > 0 ? NA : s.A, F = 3 + 2 * A;
   const SmemMap mp = make_map(F);
   float* misc = reinterpret_cast<float*>(smem + mp.misc);
   float* W1s = misc;                 // [F][H]
@@ -270,34 +284,57 @@ __global__ void __launch_bounds__(TCT, 1)
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
-  bool first_tile = true;
+  // G1^T: D=f32, A=B=tf32, K-major, M=128 (64 delta1 units + 64 ignored rows), N = n_fu
+  const uint32_t idesc_g1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(mp.n_g1 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
   // positions and reverse seed of one tile row; the next tile's are fetched while the current one computes
-  float nx = 0.f, ny = 0.f, nz = 0.f, nseed = 0.f;
+  float nx = 0.f, ny = 0.f, nz = 0.f, nwt = 1.f, ninv = 0.f;     // raw loads; consumed one tile later
   auto fetch = [&](const int64_t item) {
     const int i = (int)(item % ns);
     int64_t w = (item / ns) * ROWS + row;
-    const bool valid = w < W;
-    if (!valid) w = W - 1;
+    if (w >= W) w = W - 1;
     const int e = elec0 + i;
     nx = r[(int64_t)(3 * e + 0) * W + w];
     ny = r[(int64_t)(3 * e + 1) * W + w];
     nz = r[(int64_t)(3 * e + 2) * W + w];
-    float wt = 1.0f;
-    if (wgt != nullptr) wt = wgt[w];
-    else if (e_l != nullptr) {
-      const float ev = e_l[w];
-      wt = isfinite(ev) ? ev - centerf : 0.f;
-    }
-    nseed = wt * inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
-    if (!valid || !isfinite(nseed)) nseed = 0.f;
+    if (wgt != nullptr) nwt = wgt[w];
+    else if (e_l != nullptr) nwt = e_l[w];
+    ninv = inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
   };
   if (worker && chunk < n_items) fetch(chunk);
-  for (int64_t item = chunk; item < n_items; item += n_chunks) {
+  // Pipeline (one tile = 3 CTA barriers; delta1 of tile t stays in registers until tile t+1's first phase, so the
+  // wait for G2(t) -- which still reads the buffer delta1^T goes into -- hides behind layer 1 of tile t+1):
+  //   P1  layer 1(t) -> A(h1) in TMEM ; delta1^T(t-1) -> dT                 | issue U2(t), G1(t-1)
+  //   P2  h1^T(t) -> hT ; wait U2 ; h2, dW3, delta2 -> A(delta2) in TMEM      | issue D1(t)
+  //   P3  wait G1(t-1) ; delta2^T(t) -> dT ; features(t) -> fT              | issue G2(t)
+  //   P4  wait D1 ; delta1(t) = D1 (1 - h1^2)  (registers)
+  float d1[UPT];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) d1[j] = 0.f;
+  auto issue_g1 = [&](const uint32_t leader, const bool first) {   // G1^T += delta1 [f|1]  (M = delta1 unit, N = feature)
+    const uint64_t ah = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), al = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
+    const uint64_t bh = umma_desc(sbase + mp.fT_hi, mp.rgf, 128), bl = umma_desc(sbase + mp.fT_lo, mp.rgf, 128);
+#pragma unroll
+    for (int ks = 0; ks < ROWS / 8; ++ks) {
+      const uint64_t ao = (uint64_t)((ks * 2 * mp.rgd) >> 4), bo = (uint64_t)((ks * 2 * mp.rgf) >> 4);
+      const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+      umma_ss(tmem_base + C_G1, ah + ao, bh + bo, idesc_g1, acc, leader);
+      umma_ss(tmem_base + C_G1, al + ao, bh + bo, idesc_g1, 1u, leader);
+      umma_ss(tmem_base + C_G1, ah + ao, bl + bo, idesc_g1, 1u, leader);
+    }
+    umma_commit(bar_g, leader);
+  };
+  int64_t n_done = 0;                                  // tiles this CTA has completed
+  for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
     float h1[UPT], d2[UPT], seed = 0.f;
+    // ======== P1 ========
     if (worker) {
-      // ---- positions, seed, features, layer 1 (FP32 FFMA) --------------------------------------------------
       const float x = nx, y = ny, z = nz;
-      seed = nseed;
+      {
+        float wt = nwt;
+        if (wgt == nullptr && e_l != nullptr) wt = isfinite(nwt) ? nwt - centerf : 0.f;
+        seed = wt * ninv;
+        if ((item / ns) * ROWS + row >= W || !isfinite(seed)) seed = 0.f;
+      }
       if (item + n_chunks < n_items) fetch(item + n_chunks);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
@@ -319,6 +356,7 @@ __global__ void __launch_bounds__(TCT, 1)
         fstage[2 * FS_LD + row] = z;
         fstage[F * FS_LD + row] = 1.0f;                  // ones unit -> db1
       }
+#pragma unroll
       for (int a = 0; a < A; ++a) {
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -341,16 +379,21 @@ __global__ void __launch_bounds__(TCT, 1)
       for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
       // A operand of U2: straight into tensor memory (its previous reader, D1 of the last tile, has completed)
       stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
+      if (n_done > 0) {
+        mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
+        ph_g2 ^= 1;
+        stage_cols_smem(dT_hi, dT_lo, c0, t4, d1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- U2 = h1 W2 (A from tensor memory) ------------------------------------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       const uint64_t bh = umma_desc(sbase + mp.wa_hi, H * 16, 128), bl = umma_desc(sbase + mp.wa_lo, H * 16, 128);
 #pragma unroll
-      for (int ks = 0; ks < H / 8; ++ks) {
+      for (int ks = 0; ks < H / 8; ++ks) {               // U2 = h1 W2 (A from tensor memory)
         const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
         const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
         umma_ts(tmem_base + C_U2, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
@@ -358,24 +401,12 @@ __global__ void __launch_bounds__(TCT, 1)
         umma_ts(tmem_base + C_U2, ah, bl + bo, 1u, leader);
       }
       umma_commit(bar_u, leader);
+      if (n_done > 0) issue_g1(leader, n_done == 1);
       __syncwarp();
     }
-    // ---- while U2 runs: transposed h1 (for G2) and feature relayout (for G1); then h2, dW3, delta2 ----------------------
+    // ======== P2 ========
     if (worker) {
-      if (!first_tile) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }      // the previous tile's G1 reads the feature / delta buffers
-      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);                    // its G2 (reader of this buffer) was waited for already
-      // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
-      for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
-        const int g = idx / mp.n_fu, f = idx % mp.n_fu;     // consecutive lanes: consecutive 16-byte granules
-        const float4 fv = *reinterpret_cast<const float4*>(fstage + f * FS_LD + 4 * g);
-        float4 h4, l4;
-        split_tf32(fv.x, h4.x, l4.x);
-        split_tf32(fv.y, h4.y, l4.y);
-        split_tf32(fv.z, h4.z, l4.z);
-        split_tf32(fv.w, h4.w, l4.w);
-        *reinterpret_cast<float4*>(smem + mp.fT_hi + g * mp.rgf + f * 16) = h4;
-        *reinterpret_cast<float4*>(smem + mp.fT_lo + g * mp.rgf + f * 16) = l4;
-      }
+      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);         // G2(t-1), the reader of this buffer, was waited for in P1
       mbar_wait(bar_u, ph_u);
       ph_u ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -394,98 +425,97 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- D1 = delta2 W2^T (A from tensor memory) -----------------------------------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
-      {
-        const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
+      const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
 #pragma unroll
-        for (int ks = 0; ks < H / 8; ++ks) {
-          const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
-          const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
-          umma_ts(tmem_base + C_D1, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
-          umma_ts(tmem_base + C_D1, al, bh + bo, 1u, leader);
-          umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
-        }
+      for (int ks = 0; ks < H / 8; ++ks) {               // D1 = delta2 W2^T (A from tensor memory)
+        const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+        const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
+        umma_ts(tmem_base + C_D1, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+        umma_ts(tmem_base + C_D1, al, bh + bo, 1u, leader);
+        umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
       }
       umma_commit(bar_d, leader);
       __syncwarp();
     }
-    // ---- while D1 runs: transposed delta2 (B operand of G2) -----------------------------------------------------------------
+    // ======== P3 ========
     if (worker) {
+      if (n_done > 0) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }   // G1(t-1) reads delta1^T(t-1) and the features of tile t-1
       stage_cols_smem(dT_hi, dT_lo, c0, t4, d2);
+      // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
+      for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
+        const int g = idx / mp.n_fu, f = idx % mp.n_fu;     // consecutive lanes: consecutive 16-byte granules
+        const float4 fv = *reinterpret_cast<const float4*>(fstage + f * FS_LD + 4 * g);
+        float4 h4, l4;
+        split_tf32(fv.x, h4.x, l4.x);
+        split_tf32(fv.y, h4.y, l4.y);
+        split_tf32(fv.z, h4.z, l4.z);
+        split_tf32(fv.w, h4.w, l4.w);
+        *reinterpret_cast<float4*>(smem + mp.fT_hi + g * mp.rgf + f * 16) = h4;
+        *reinterpret_cast<float4*>(smem + mp.fT_lo + g * mp.rgf + f * 16) = l4;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    // ---- G2 += [h1|1]^T delta2 ------------------------------------------------------------------------------------------
     if (warp == TCW / 32) {
       const uint32_t leader = elect_one();
-      {
-        const uint64_t ah = umma_desc(sbase + mp.hT_hi, mp.rgh, 128), al = umma_desc(sbase + mp.hT_lo, mp.rgh, 128);
-        const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
+      const uint64_t ah = umma_desc(sbase + mp.hT_hi, mp.rgh, 128), al = umma_desc(sbase + mp.hT_lo, mp.rgh, 128);
+      const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
 #pragma unroll
-        for (int ks = 0; ks < ROWS / 8; ++ks) {
-          const uint64_t ao = (uint64_t)((ks * 2 * mp.rgh) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
-          const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
-          umma_ss(tmem_base + C_G2, ah + ao, bh + bo, acc, leader);
-          umma_ss(tmem_base + C_G2, al + ao, bh + bo, 1u, leader);
-          umma_ss(tmem_base + C_G2, ah + ao, bl + bo, 1u, leader);
-        }
+      for (int ks = 0; ks < ROWS / 8; ++ks) {            // G2 += [h1|1]^T delta2
+        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgh) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
+        const uint32_t acc = (n_done == 0 && ks == 0) ? 0u : 1u;
+        umma_ss(tmem_base + C_G2, ah + ao, bh + bo, IDESC, acc, leader);
+        umma_ss(tmem_base + C_G2, al + ao, bh + bo, IDESC, 1u, leader);
+        umma_ss(tmem_base + C_G2, ah + ao, bl + bo, IDESC, 1u, leader);
       }
       umma_commit(bar_g2, leader);
       __syncwarp();
     }
-    // ---- delta1 = D1 (1 - h1^2) -----------------------------------------------------------------------------------
+    // ======== P4 ========
     if (worker) {
       mbar_wait(bar_d, ph_d);
       ph_d ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float v[16];
-      tmem_ld16(tmem_base + lane_base + C_D1 + (uint32_t)c0, v);
+      tmem_ld16(tmem_base + lane_base + C_D1 + (uint32_t)c0, d1);
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) v[j] *= fmaf(-h1[j], h1[j], 1.0f);
-      mbar_wait(bar_g2, ph_g2);                        // G2 still reads delta2^T from the buffer delta1^T goes into
+      for (int j = 0; j < UPT; ++j) d1[j] *= fmaf(-h1[j], h1[j], 1.0f);
+    }
+  }
+  // ---- drain: delta1^T of the last tile, its G1 -----------------------------------------------------------------------
+  const bool any = n_done > 0;
+  if (any) {
+    if (worker) {
+      mbar_wait(bar_g2, ph_g2);
       ph_g2 ^= 1;
-      stage_cols_smem(dT_hi, dT_lo, c0, t4, v);
+      stage_cols_smem(dT_hi, dT_lo, c0, t4, d1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- G1 += [f|1]^T delta1 --------------------------------------------------------------------------------------
     if (warp == TCW / 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
-      const uint64_t ah = umma_desc(sbase + mp.fT_hi, mp.rgf, 128), al = umma_desc(sbase + mp.fT_lo, mp.rgf, 128);
-      const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
-#pragma unroll
-      for (int ks = 0; ks < ROWS / 8; ++ks) {
-        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgf) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
-        const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
-        umma_ss(tmem_base + C_G1, ah + ao, bh + bo, acc, leader);
-        umma_ss(tmem_base + C_G1, al + ao, bh + bo, 1u, leader);
-        umma_ss(tmem_base + C_G1, ah + ao, bl + bo, 1u, leader);
-      }
-      umma_commit(bar_g, leader);
+      issue_g1(leader, n_done == 1);
       __syncwarp();
     }
-    first_tile = false;
   }
 
-  // ---- flush: G2 -> dW2 (+db2), G1 -> dW1 (+db1), register partials -> dW3, db3 --------------------------------------
+  // ---- flush: G2 -> dW2 (+db2), G1^T -> dW1 (+db1), register partials -> dW3, db3 ------------------------------------
   float* slab = part + (int64_t)blockIdx.x * p_mlp;
   const int o_b1 = 0, o_W1 = H, o_b2 = H + F * H, o_W2 = o_b2 + H, o_b3 = o_W2 + H * H, o_W3 = o_b3 + 1;
   if (worker) {
-    float v2[16], v1[16];
-    if (!first_tile) {
-      mbar_wait(bar_g, ph_g);
+    float v2[16];
+    if (any) {
+      mbar_wait(bar_g, ph_g);                            // the last commit: every MMA of this CTA has completed
       ph_g ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)c0, v2);   // lane = h1 unit (row 64: ones -> db2)
-      tmem_ld16(tmem_base + lane_base + C_G1 + (uint32_t)c0, v1);   // lane = feature   (row F : ones -> db1)
     } else {
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) v2[j] = v1[j] = 0.f;             // this CTA had no tile: the slab must still be defined
+      for (int j = 0; j < UPT; ++j) v2[j] = 0.f;          // this CTA had no tile: the slab must still be defined
     }
     if (row < H) {
 #pragma unroll
@@ -494,12 +524,22 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
       for (int j = 0; j < UPT; ++j) slab[o_b2 + c0 + j] = v2[j];
     }
-    if (row < F) {
+    // G1^T: lane = delta1 unit, column = feature (column F: ones -> db1); 8 columns per read, groups dealt over quarters
+    for (int cg = quarter; cg < mp.n_g1 / 8; cg += NQ) {
+      float v1[8];
+      if (any) tmem_ld8(tmem_base + lane_base + C_G1 + (uint32_t)(8 * cg), v1);
+      else {
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) slab[o_W1 + row * H + c0 + j] = v1[j];
-    } else if (row == F) {
+        for (int j = 0; j < 8; ++j) v1[j] = 0.f;
+      }
+      if (row < H) {
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) slab[o_b1 + c0 + j] = v1[j];
+        for (int j = 0; j < 8; ++j) {
+          const int f = 8 * cg + j;
+          if (f < F) slab[o_W1 + f * H + row] = v1[j];
+          else if (f == F) slab[o_b1 + row] = v1[j];
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {                     // dW3 / db3: reduce the per-row partials over the 128 rows
@@ -518,10 +558,27 @@ __global__ void __launch_bounds__(TCT, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+template <int NA>
+int launch_t(nqmc_ctx* ctx, const SmemMap& mp, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
+             int n_chunks, cudaStream_t st) {
+  const DevSys& s = ctx->sys;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    NQMC_CUDA(cudaFuncSetAttribute(orb_bwd_tc_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  {
+    ProfScope ps(ctx, NQ_PROF_BWD, st);
+    orb_bwd_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
+                                                                     n_chunks, ctx->p_mlp);
+  }
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
 }  // namespace
 
-// returns NQMC_ERR_UNSUPPORTED when this variant does not apply (the caller then uses the FFMA kernel).
-// On success the per-CTA slabs are in ctx->part_mlp, *n_chunks_out CTAs per network.
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                          int* n_chunks_out, cudaStream_t st) {
   const DevSys& s = ctx->sys;
@@ -530,24 +587,19 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   if (mp.total > SMEM_LIMIT || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
   if (const char* e = getenv("NQMC_TC_BWD"))
     if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
-  static bool configured_dev[64] = {};
-  bool& configured = configured_dev[ctx->device & 63];
-  if (!configured) {
-    NQMC_CUDA(cudaFuncSetAttribute(orb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks * s.n_mlp > ctx->n_cta_bwd) n_chunks = ctx->n_cta_bwd / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
-  {
-    ProfScope ps(ctx, NQ_PROF_BWD, st);
-    orb_bwd_tc_kernel<<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
-                                                                 n_chunks, ctx->p_mlp);
-  }
-  NQMC_LAUNCH_CHECK();
   *n_chunks_out = n_chunks;
-  return NQMC_OK;
+  switch (s.A) {
+    case 1: return launch_t<1>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+    case 2: return launch_t<2>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+    case 3: return launch_t<3>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+    case 4: return launch_t<4>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+    case 6: return launch_t<6>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+    default: return launch_t<0>(ctx, mp, r, wgt, hdr, e_l, W, n_chunks, st);
+  }
 }
