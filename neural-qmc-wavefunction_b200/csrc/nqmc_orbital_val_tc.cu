@@ -82,6 +82,8 @@ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   lo = a - hi;
 }
 
+// NA = number of nuclei when > 0 (feature loop fully unrolled), 0 = run-time count
+template <int NA>
 __global__ void __launch_bounds__(TCT, 1)
     orb_eval1_tc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
                         float* __restrict__ phi, const int n_chunks) {
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(TCT, 1)
   uint8_t* Whi = smem;                                   // [k/4][j][k%4]
   uint8_t* Wlo = smem + WB;
   float* W1s = reinterpret_cast<float*>(smem + 2 * WB);  // [F][H]
-  const int F = s.F, A = s.A;
+  const int A = NA > 0 ? NA : s.A, F = 3 + 2 * A;
   float* b1s = W1s + F * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
@@ -147,11 +149,18 @@ __global__ void __launch_bounds__(TCT, 1)
   const int64_t n_items = nwb * ns;
 
   // layer 1 of tile `it` for this thread's (row, 16 units) -> tf32 hi/lo into the A columns of buffer b
-  auto produce = [&](int64_t it, int b) {
+  float nx = 0.f, ny = 0.f, nz = 0.f;                    // positions of the tile produced next, fetched one tile ahead
+  auto fetch = [&](int64_t it) {
     int64_t w = (it / ns) * ROWS + row;
     if (w >= W) w = W - 1;
     const int e = elec0 + (int)(it % ns);
-    const float x = r[(int64_t)(3 * e + 0) * W + w], y = r[(int64_t)(3 * e + 1) * W + w], z = r[(int64_t)(3 * e + 2) * W + w];
+    nx = r[(int64_t)(3 * e + 0) * W + w];
+    ny = r[(int64_t)(3 * e + 1) * W + w];
+    nz = r[(int64_t)(3 * e + 2) * W + w];
+  };
+  auto produce = [&](int64_t it, int b) {
+    const float x = nx, y = ny, z = nz;
+    if (it + n_chunks < n_items) fetch(it + n_chunks);
     float h1[UPT];
 #pragma unroll
     for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(TCT, 1)
         h1[4 * v + 3] = fmaf(pc[d], wv.w, h1[4 * v + 3]);
       }
     }
+#pragma unroll
     for (int a = 0; a < A; ++a) {
       const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
       const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -213,7 +223,10 @@ __global__ void __launch_bounds__(TCT, 1)
   // ---- software pipeline, depth 2 -------------------------------------------------------------------------------
   int b = 0;
   if (chunk < n_items) {
-    if (worker) produce(chunk, 0);
+    if (worker) {
+      fetch(chunk);
+      produce(chunk, 0);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == TCW / 32) issue(0);
@@ -250,27 +263,41 @@ __global__ void __launch_bounds__(TCT, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+template <int NA>
+int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, int n_chunks, size_t smem, cudaStream_t st) {
+  const DevSys& s = ctx->sys;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    NQMC_CUDA(cudaFuncSetAttribute(orb_eval1_tc_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  {
+    ProfScope ps(ctx, NQ_PROF_EVAL1, st);
+    orb_eval1_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+  }
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
 }  // namespace
 
 int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
   const DevSys& s = ctx->sys;
   if (s.H != H) return NQMC_ERR_UNSUPPORTED;
   const size_t smem = 2 * WB + ((size_t)s.F * H + 3 * H + 2 * (NQ - 1) * ROWS) * 4 + 64;
-  static bool configured_dev[64] = {};
-  bool& configured = configured_dev[ctx->device & 63];
-  if (!configured) {
-    NQMC_CUDA(cudaFuncSetAttribute(orb_eval1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  if (smem > 96 * 1024) return NQMC_ERR_UNSUPPORTED;
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
-  {
-    ProfScope ps(ctx, NQ_PROF_EVAL1, st);
-    orb_eval1_tc_kernel<<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+  switch (s.A) {
+    case 1: return launch_t<1>(ctx, r, W, phi, n_chunks, smem, st);
+    case 2: return launch_t<2>(ctx, r, W, phi, n_chunks, smem, st);
+    case 3: return launch_t<3>(ctx, r, W, phi, n_chunks, smem, st);
+    case 4: return launch_t<4>(ctx, r, W, phi, n_chunks, smem, st);
+    case 6: return launch_t<6>(ctx, r, W, phi, n_chunks, smem, st);
+    default: return launch_t<0>(ctx, r, W, phi, n_chunks, smem, st);
   }
-  NQMC_LAUNCH_CHECK();
-  return NQMC_OK;
 }
