@@ -28,7 +28,8 @@ namespace {
 constexpr int H = 64;
 constexpr int NQ = 4;                 // threads per row
 constexpr int TCW = 128 * NQ;         // worker threads
-constexpr int TCT = TCW + 32;         // + MMA issuer warp
+constexpr int TCT = TCW;              // 16 warps -> 128 registers per thread (a 17th warp would cap them at 96 and spill)
+constexpr int ISSUER = TCW / 32 - 1;  // the last worker warp also issues the MMAs (one elected lane, predicated)
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
 constexpr uint32_t TMEM_COLS = 512;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == TCW / 32) {
+    if (warp == ISSUER) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       const uint64_t bh = umma_desc(sbase + mp.wa_hi, H * 16, 128), bl = umma_desc(sbase + mp.wa_lo, H * 16, 128);
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == TCW / 32) {
+    if (warp == ISSUER) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(TCT, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (warp == TCW / 32) {
+    if (warp == ISSUER) {
       const uint32_t leader = elect_one();
       const uint64_t ah = umma_desc(sbase + mp.hT_hi, mp.rgh, 128), al = umma_desc(sbase + mp.hT_lo, mp.rgh, 128);
       const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == TCW / 32) {
+    if (warp == ISSUER) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t leader = elect_one();
       issue_g1(leader, n_done == 1);
