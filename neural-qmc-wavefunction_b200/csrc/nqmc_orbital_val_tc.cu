@@ -17,7 +17,8 @@ namespace {
 constexpr int H = 64;
 constexpr int NQ = 4;
 constexpr int TCW = 128 * NQ;
-constexpr int TCT = TCW + 32;
+constexpr int TCT = TCW;              // 16 warps: 128 registers per thread
+constexpr int ISSUER = TCW / 32 - 1;  // the last worker warp also issues the MMAs
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;
 constexpr uint32_t TMEM_COLS = 512;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == TCW / 32) issue(0);
+    if (warp == ISSUER) issue(0);
   }
   for (int64_t item = chunk; item < n_items; item += n_chunks, b ^= 1) {
     const int64_t next = item + n_chunks;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                        // A columns of `next` staged; accumulator b read; partials visible
-    if (warp == TCW / 32 && next < n_items) issue(b ^ 1);
+    if (warp == ISSUER && next < n_items) issue(b ^ 1);
     if (worker && quarter == 0) {
       const int64_t wr = (item / ns) * ROWS + row;
       if (wr < W) {
