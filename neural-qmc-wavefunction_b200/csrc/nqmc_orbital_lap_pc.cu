@@ -205,16 +205,15 @@ __global__ void __launch_bounds__(TCT, 1)
       const int64_t w0 = (item / ns) * ROWS;
       const float x = nx, y = ny, z = nz;
       if (item + n_chunks < n_items) fetch(item + n_chunks);
-      // features of this row with gradient / Laplacian, in registers for all 8 chunks
-      float fd[NA][CH], fe[NA][CH];
+      // per nucleus: d, exp(-d), unit vector, 2/d -- in registers for all 8 chunks.  With s = wd - e we the five
+      // channels of (d, e) contribute  value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we   (7 FMA, not 10).
+      float fdd[NA], fex[NA], fux[NA], fuy[NA], fuz[NA], fti[NA];
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        const float ex = __expf(-dd), inv = 1.0f / dd;
-        const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
-        fd[a][0] = dd; fd[a][1] = ux; fd[a][2] = uy; fd[a][3] = uz; fd[a][4] = 2.0f * inv;
-        fe[a][0] = ex; fe[a][1] = -ex * ux; fe[a][2] = -ex * uy; fe[a][3] = -ex * uz; fe[a][4] = ex * (1.0f - 2.0f * inv);
+        const float inv = 1.0f / dd;
+        fdd[a] = dd; fex[a] = __expf(-dd); fux[a] = dx * inv; fuy[a] = dy * inv; fuz[a] = dz * inv; fti[a] = 2.0f * inv;
       }
 #pragma unroll 1
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
@@ -225,6 +224,7 @@ __global__ void __launch_bounds__(TCT, 1)
           acc[0][0] = bv.x; acc[0][1] = bv.y;
 #pragma unroll
           for (int c = 1; c < CH; ++c) acc[c][0] = acc[c][1] = 0.f;
+          float ew[UPT] = {0.f, 0.f};                            // sum_a e_a we_a : part of the value and of the Laplacian
           const float pc[3] = {x, y, z};
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
@@ -238,18 +238,24 @@ __global__ void __launch_bounds__(TCT, 1)
           for (int a = 0; a < NA; ++a) {
             const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
             const float2 we = *reinterpret_cast<const float2*>(W1s + (3 + NA + a) * H + j0);
+            const float wdv[UPT] = {wd.x, wd.y}, wev[UPT] = {we.x, we.y};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              acc[c][0] = fmaf(fd[a][c], wd.x, fmaf(fe[a][c], we.x, acc[c][0]));
-              acc[c][1] = fmaf(fd[a][c], wd.y, fmaf(fe[a][c], we.y, acc[c][1]));
+            for (int u2 = 0; u2 < UPT; ++u2) {
+              ew[u2] = fmaf(fex[a], wev[u2], ew[u2]);
+              acc[0][u2] = fmaf(fdd[a], wdv[u2], acc[0][u2]);
+              const float sv = fmaf(-fex[a], wev[u2], wdv[u2]);
+              acc[1][u2] = fmaf(fux[a], sv, acc[1][u2]);
+              acc[2][u2] = fmaf(fuy[a], sv, acc[2][u2]);
+              acc[3][u2] = fmaf(fuz[a], sv, acc[3][u2]);
+              acc[4][u2] = fmaf(fti[a], sv, acc[4][u2]);
             }
           }
 #pragma unroll
-          for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules
-            const float h = nq_tanh(acc[0][u2]);
-            const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
+          for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules: lap' = tp (lap - 2 h |grad|^2)
+            const float h = nq_tanh(acc[0][u2] + ew[u2]);
+            const float tp = fmaf(-h, h, 1.0f);
             const float g2 = fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
-            acc[4][u2] = fmaf(tp, acc[4][u2], tpp * g2);
+            acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + ew[u2]);
             acc[1][u2] *= tp; acc[2][u2] *= tp; acc[3][u2] *= tp;
             acc[0][u2] = h;
           }
@@ -289,14 +295,14 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float h = nq_tanh(v[0][j] + b2s[c0 + j]);
-          const float tp = fmaf(-h, h, 1.0f), tpp = -2.0f * h * tp;
+          const float tp = fmaf(-h, h, 1.0f);
           const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
           const float w3 = W3s[c0 + j], w3tp = w3 * tp;
           out[0] = fmaf(w3, h, out[0]);
           out[1] = fmaf(w3tp, v[1][j], out[1]);
           out[2] = fmaf(w3tp, v[2][j], out[2]);
           out[3] = fmaf(w3tp, v[3][j], out[3]);
-          out[4] = fmaf(w3, fmaf(tp, v[4][j], tpp * g2), out[4]);
+          out[4] = fmaf(w3tp, fmaf(-(h + h), g2, v[4][j]), out[4]);
         }
       }
       if (quarter != 0) {
