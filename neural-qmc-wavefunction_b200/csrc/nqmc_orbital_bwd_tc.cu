@@ -235,18 +235,28 @@ __global__ void __launch_bounds__(TCT, 1)
     W3s[q] = theta[off.W3 + q];
   }
   for (int q = tid; q < H + 8; q += TCT) redS[q] = 0.f;
-  for (int idx = tid; idx < H * H; idx += TCT) {
-    const int k = idx / H, j = idx % H;
-    float hi, lo;
-    split_tf32(theta[off.W2 + idx], hi, lo);
-    // copy a: B[n=j][kk=k] (for U2 = h1 W2)      -> [k/4][j][k%4]
-    const int oa = (k >> 2) * (H * 4) + j * 4 + (k & 3);
-    reinterpret_cast<float*>(smem + mp.wa_hi)[oa] = hi;
-    reinterpret_cast<float*>(smem + mp.wa_lo)[oa] = lo;
-    // copy b: B[n=k][kk=j] (for D1 = delta2 W2^T) -> [j/4][k][j%4]
-    const int ob = (j >> 2) * (H * 4) + k * 4 + (j & 3);
-    reinterpret_cast<float*>(smem + mp.wb_hi)[ob] = hi;
-    reinterpret_cast<float*>(smem + mp.wb_lo)[ob] = lo;
+  {
+    // all loads of a thread in flight at once: with a cold L2 each dependent round trip costs ~1 us
+    constexpr int NL = H * H / TCT;
+    static_assert(NL * TCT == H * H, "W2 staging assumes the block size divides H*H");
+    float wv[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) wv[i] = theta[off.W2 + tid + i * TCT];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * TCT;
+      const int k = idx / H, j = idx % H;
+      float hi, lo;
+      split_tf32(wv[i], hi, lo);
+      // copy a: B[n=j][kk=k] (for U2 = h1 W2)      -> [k/4][j][k%4]
+      const int oa = (k >> 2) * (H * 4) + j * 4 + (k & 3);
+      reinterpret_cast<float*>(smem + mp.wa_hi)[oa] = hi;
+      reinterpret_cast<float*>(smem + mp.wa_lo)[oa] = lo;
+      // copy b: B[n=k][kk=j] (for D1 = delta2 W2^T) -> [j/4][k][j%4]
+      const int ob = (j >> 2) * (H * 4) + k * 4 + (j & 3);
+      reinterpret_cast<float*>(smem + mp.wb_hi)[ob] = hi;
+      reinterpret_cast<float*>(smem + mp.wb_lo)[ob] = lo;
+    }
   }
   __syncthreads();
   // the ones unit (index 64) of the transposed h1 buffer -> row 64 of G2 = db2 ; hi = 1, lo stays 0

@@ -116,13 +116,23 @@ __global__ void __launch_bounds__(TCT, 1)
     b2s[q] = theta[off.b2 + q];
     W3s[q] = theta[off.W3 + q];
   }
-  for (int idx = tid; idx < H * H; idx += TCT) {
-    const int k = idx / H, j = idx % H;
-    float hi, lo;
-    split_tf32(theta[off.W2 + idx], hi, lo);
-    const int o = (k >> 2) * (H * 4) + j * 4 + (k & 3);
-    reinterpret_cast<float*>(Whi)[o] = hi;
-    reinterpret_cast<float*>(Wlo)[o] = lo;
+  {
+    // all loads of a thread in flight at once: with a cold L2 each dependent round trip costs ~1 us
+    constexpr int NL = H * H / TCT;
+    static_assert(NL * TCT == H * H, "W2 staging assumes the block size divides H*H");
+    float wv[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) wv[i] = theta[off.W2 + tid + i * TCT];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * TCT;
+      const int k = idx / H, j = idx % H;
+      float hi, lo;
+      split_tf32(wv[i], hi, lo);
+      const int o = (k >> 2) * (H * 4) + j * 4 + (k & 3);
+      reinterpret_cast<float*>(Whi)[o] = hi;
+      reinterpret_cast<float*>(Wlo)[o] = lo;
+    }
   }
   const float b3 = theta[off.b3];
   if (tid == 0) {
