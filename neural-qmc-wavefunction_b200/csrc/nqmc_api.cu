@@ -210,6 +210,9 @@ int nqmc_destroy(nqmc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   free_scratch(ctx);
   if (ctx->theta) cudaFree(ctx->theta);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
+  if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
   delete ctx;
   return NQMC_OK;
 }
@@ -522,16 +525,30 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
     uni = ctx->uni_stage;
   }
   NQMC_CUDA(cudaMemcpyAsync(ctx->logp_stage, logp, w * f, cudaMemcpyHostToDevice, st));
-  rc = nqmc_walker_step(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
-                        ctx->hdr_stage, ctx->gsum_stage, st_);
+  rc = nqmc_walker_step_a(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
+                          ctx->hdr_stage, st_);
   if (rc) return rc;
-  rc = nq_aos_soa(ctx, ctx->r_soa, ctx->aos_stage, W, false, st);
+  // walkers, log|psi|, E_L and the header are final after phase A: send them home on a side stream while the
+  // reverse pass (phase B) runs on the caller's stream
+  if (!ctx->side_stream) {
+    NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_phase_a, cudaEventDisableTiming));
+    NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
+  }
+  cudaStream_t sd = ctx->side_stream;
+  NQMC_CUDA(cudaEventRecord(ctx->ev_phase_a, st));
+  NQMC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_phase_a, 0));
+  rc = nq_aos_soa(ctx, ctx->r_soa, ctx->aos_stage, W, false, sd);
   if (rc) return rc;
-  NQMC_CUDA(cudaMemcpyAsync(r_aos, ctx->aos_stage, nn * w * f, cudaMemcpyDeviceToHost, st));
-  NQMC_CUDA(cudaMemcpyAsync(logp, ctx->logp_stage, w * f, cudaMemcpyDeviceToHost, st));
-  NQMC_CUDA(cudaMemcpyAsync(e_l, ctx->e_scratch, w * f, cudaMemcpyDeviceToHost, st));
-  NQMC_CUDA(cudaMemcpyAsync(hdr, ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaMemcpyAsync(r_aos, ctx->aos_stage, nn * w * f, cudaMemcpyDeviceToHost, sd));
+  NQMC_CUDA(cudaMemcpyAsync(logp, ctx->logp_stage, w * f, cudaMemcpyDeviceToHost, sd));
+  NQMC_CUDA(cudaMemcpyAsync(e_l, ctx->e_scratch, w * f, cudaMemcpyDeviceToHost, sd));
+  NQMC_CUDA(cudaMemcpyAsync(hdr, ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double), cudaMemcpyDeviceToHost, sd));
+  NQMC_CUDA(cudaEventRecord(ctx->ev_side_done, sd));
+  rc = nqmc_walker_step_b(ctx, ctx->r_soa, ctx->e_scratch, W, ctx->hdr_stage, ctx->gsum_stage, st_);
+  if (rc) return rc;
   NQMC_CUDA(cudaMemcpyAsync(gsum, ctx->gsum_stage, (size_t)ctx->sys.P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  NQMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_done, 0));   // the next call on this stream reuses the staging buffers
   NQMC_CUDA(cudaStreamSynchronize(st));
   return NQMC_OK;
 }

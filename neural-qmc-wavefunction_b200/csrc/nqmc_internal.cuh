@@ -94,6 +94,9 @@ struct nqmc_ctx {
   static constexpr int PROF_KINDS = 6, PROF_RING = 512;
   cudaEvent_t prof_ev[PROF_KINDS][PROF_RING][2] = {};
   int prof_n[PROF_KINDS] = {};
+  // host entry point: results of phase A travel back on a side stream while phase B (the reverse pass) runs
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_phase_a = nullptr, ev_side_done = nullptr;
 };
 enum { NQ_PROF_EVAL1 = 0, NQ_PROF_EVAL5 = 1, NQ_PROF_BWD = 2, NQ_PROF_ASSEMBLE = 3, NQ_PROF_ACCEPT = 4, NQ_PROF_MISC = 5 };
 
