@@ -141,6 +141,9 @@ def run_ours(args):
     ctx = wf.context(mol)
     ctx.set_params(theta)
     ctx.reserve(Wl)
+    # N > 1: hdr / gsum are summed over ranks inside nqmc_walker_step by the peer-memory all-reduce (NVLink);
+    # NQMC_COMM=nccl keeps the two NCCL all-reduces around the rank-local halves instead (A/B runs)
+    peer = world > 1 and os.environ.get("NQMC_COMM", "peer") != "nccl" and parallel.attach_peer_memory(ctx)
     r = ctx.to_soa(initial_walkers(mol, Wl, lo))
     _, la = ctx.log_psi(r)
     logp = (2.0 * la).contiguous()
@@ -157,6 +160,9 @@ def run_ours(args):
     def one_step():
         s = step_no[0]
         step_no[0] += 1
+        if peer:
+            ctx.walker_step(r, logp, SIGMA, e_l, hdr, gsum, seed=SEED, step=s, walker_id0=lo, n_accepted=nacc)
+            return
         ctx.walker_step_a(r, logp, SIGMA, e_l, hdr, seed=SEED, step=s, walker_id0=lo, n_accepted=nacc)
         if world > 1:
             dist.all_reduce(hdr)
@@ -214,7 +220,7 @@ def run_ours(args):
     d2h = Wl * nn * 4 + Wl * 4 + Wl * 4 + 8 * 8 + ctx.P * 8
 
     def e2e_step(s):
-        if world == 1:                                         # the C-ABI host entry point itself
+        if world == 1 or peer:                                 # the C-ABI host entry point itself
             ctx.walker_step_host(r_host.numpy(), logp_host.numpy(), SIGMA, e_host.numpy(), hdr_host.numpy(),
                                  g_host.numpy(), seed=SEED, step=s, walker_id0=lo)
         else:                                                  # same copies, phases split around the all-reduces
@@ -270,10 +276,12 @@ def run_ours(args):
                        "walkers_per_gpu": Wl, "global_walkers": world * Wl, "step_size": SIGMA,
                        "rng": "device Philox4x32-10", "l2": "256 MiB flush write between timed steps",
                        "parallelism": f"walkers sharded over {world} GPU(s); all-reduce hdr(8 f64)+grad(P f64) per step",
+                       "collective": ("none" if world == 1 else "peer-memory one-shot all-reduce inside nqmc_walker_step (NVLink)"
+                                      if peer else "NCCL all_reduce x2"),
                        "algorithmic_flop_per_walker_step": flops_step},
             "clocks": clocks,
             "e2e": {"value": world * Wl * args.steps / e2e_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if world == 1
+                    "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if (world == 1 or peer)
                     else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host"},
             "gpu_launches": launches,
             "roofline": ({"bound": "tensor", "kernel": "orb_eval5_tc_kernel (orbital forward value+grad+Laplacian; H x H layer = tcgen05 3xTF32, input layer = FFMA)",

@@ -196,6 +196,23 @@ int nqmc_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, nqmc_stream stream);
 int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t walker_id0, int64_t W, float* normals,
                   float* uniforms, nqmc_stream stream);
 
+
+/* ---- multi-GPU: peer-memory communicator (one process per GPU on one node) -----------------------------------
+ * The reference is single-device.  Sharding its walker loop needs two sums over ranks per step:
+ * the statistics header before the reverse pass (global mean of E_L, src/nqmc/optimizer/vmc.py:113-126) and the
+ * gradient sum after it (vmc.py:126-133).  nqmc_comm_create allocates this rank's inbox and returns an opaque
+ * handle (NQMC_COMM_HANDLE_BYTES bytes) to exchange by any out-of-band means (torch.distributed all_gather in
+ * nqmc_b200/parallel.py); nqmc_comm_attach maps the peers' inboxes (handles = world x NQMC_COMM_HANDLE_BYTES bytes,
+ * rank order).  Once attached, nqmc_walker_step / nqmc_walker_step_host reduce hdr and gsum over all ranks in-stream
+ * (one-shot push all-reduce over NVLink, summed in rank order: bitwise identical on every rank); the _a/_b halves
+ * stay rank-local so a caller can use its own collective instead.  All ranks must make the same calls in the same
+ * order.  world <= 8. */
+#define NQMC_COMM_HANDLE_BYTES 64
+int nqmc_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out);
+int nqmc_comm_attach(nqmc_ctx* ctx, const void* handles);
+/* In-place sum over ranks of vec[0..len), len <= max(param_count, NQMC_HDR_SIZE). */
+int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

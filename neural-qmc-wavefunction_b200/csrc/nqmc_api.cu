@@ -210,6 +210,7 @@ int nqmc_destroy(nqmc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   free_scratch(ctx);
   if (ctx->theta) cudaFree(ctx->theta);
+  nq_comm_free(ctx);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
@@ -497,7 +498,30 @@ int nqmc_walker_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals,
                      double* gsum, nqmc_stream st) {
   int rc = nqmc_walker_step_a(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, e_l, n_acc, hdr, st);
   if (rc) return rc;
-  return nqmc_walker_step_b(ctx, r, e_l, W, hdr, gsum, st);
+  const bool multi = nq_comm_active(ctx);
+  if (multi && (rc = nq_comm_allreduce(ctx, hdr, NQMC_HDR_SIZE, S(st)))) return rc;   // global mean for the centring
+  rc = nqmc_walker_step_b(ctx, r, e_l, W, hdr, gsum, st);
+  if (rc) return rc;
+  if (multi) rc = nq_comm_allreduce(ctx, gsum, ctx->sys.P, S(st));
+  return rc;
+}
+
+int nqmc_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out) {
+  if (!ctx) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_comm_create(ctx, rank, world, handle_out);
+}
+
+int nqmc_comm_attach(nqmc_ctx* ctx, const void* handles) {
+  if (!ctx) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_comm_attach(ctx, handles);
+}
+
+int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream st) {
+  if (!ctx) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_comm_allreduce(ctx, vec, len, S(st));
 }
 
 int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float* normals_aos, const float* uniforms,
@@ -528,6 +552,8 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
   rc = nqmc_walker_step_a(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
                           ctx->hdr_stage, st_);
   if (rc) return rc;
+  const bool multi = nq_comm_active(ctx);
+  if (multi && (rc = nq_comm_allreduce(ctx, ctx->hdr_stage, NQMC_HDR_SIZE, st))) return rc;
   // walkers, log|psi|, E_L and the header are final after phase A: send them home on a side stream while the
   // reverse pass (phase B) runs on the caller's stream
   if (!ctx->side_stream) {
@@ -547,6 +573,7 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
   NQMC_CUDA(cudaEventRecord(ctx->ev_side_done, sd));
   rc = nqmc_walker_step_b(ctx, ctx->r_soa, ctx->e_scratch, W, ctx->hdr_stage, ctx->gsum_stage, st_);
   if (rc) return rc;
+  if (multi && (rc = nq_comm_allreduce(ctx, ctx->gsum_stage, ctx->sys.P, st))) return rc;
   NQMC_CUDA(cudaMemcpyAsync(gsum, ctx->gsum_stage, (size_t)ctx->sys.P * sizeof(double), cudaMemcpyDeviceToHost, st));
   NQMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_done, 0));   // the next call on this stream reuses the staging buffers
   NQMC_CUDA(cudaStreamSynchronize(st));

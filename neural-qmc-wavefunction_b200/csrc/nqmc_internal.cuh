@@ -18,6 +18,9 @@
 // ---------------------------------------------------------------------------------------------
 // Parameter map: offsets of every block inside the flat theta vector (sorted-key pytree order;
 // inside one flax Dense, 'bias' sorts before 'kernel').
+constexpr int NQ_COMM_MAX_WORLD = 8;
+struct nq_comm;
+
 struct MlpOff {     // one Dense(F,H)-tanh-Dense(H,H)-tanh-Dense(H,1) network
   int b1, W1, b2, W2, b3, W3;
 };
@@ -95,6 +98,7 @@ struct nqmc_ctx {
   cudaEvent_t prof_ev[PROF_KINDS][PROF_RING][2] = {};
   int prof_n[PROF_KINDS] = {};
   // host entry point: results of phase A travel back on a side stream while phase B (the reverse pass) runs
+  struct nq_comm* comm = nullptr;   // peer-memory communicator (nqmc_comm.cu); nullptr: single GPU or NCCL outside
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_phase_a = nullptr, ev_side_done = nullptr;
 };
@@ -192,6 +196,12 @@ int nq_simple_logpsi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, cu
 int nq_simple_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
 int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                     int64_t W, double* out, cudaStream_t st);
+// peer-memory communicator (nqmc_comm.cu)
+int nq_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out);
+int nq_comm_attach(nqmc_ctx* ctx, const void* handles);
+int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st);
+bool nq_comm_active(const nqmc_ctx* ctx);
+void nq_comm_free(nqmc_ctx* ctx);
 int nq_aos_soa(nqmc_ctx* ctx, const float* src, float* dst, int64_t W, bool to_soa, cudaStream_t st);
 int nq_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, float* normals, float* uniforms,
                 cudaStream_t st);

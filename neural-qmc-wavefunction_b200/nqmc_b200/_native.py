@@ -26,6 +26,7 @@ EXPORTS = [
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
     "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
+    "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce",
 ]
 
 
@@ -90,6 +91,9 @@ def load_library():
     lib.nqmc_use_tensor_cores.argtypes = [vp, C.c_int]
     lib.nqmc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.nqmc_ffma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp]
+    lib.nqmc_comm_create.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.nqmc_comm_attach.argtypes = [vp, vp]
+    lib.nqmc_comm_allreduce.argtypes = [vp, vp, i64, vp]
     _lib = lib
     return lib
 
@@ -295,6 +299,25 @@ class Context:
                                                    np_ptr(uniforms), int(seed) & (2**64 - 1), int(step), int(walker_id0),
                                                    float(sigma), W, e_l.ctypes.data, hdr.ctypes.data, gsum.ctypes.data,
                                                    self.stream), "nqmc_walker_step_host")
+
+    # ---- multi-GPU: peer-memory communicator (include/nqmc_b200.h, "multi-GPU") ----
+    COMM_HANDLE_BYTES = 64
+
+    def comm_create(self, rank: int, world: int) -> bytes:
+        """Allocate this rank's inbox; returns the opaque handle to hand to every peer."""
+        buf = C.create_string_buffer(self.COMM_HANDLE_BYTES)
+        self._check(self.lib.nqmc_comm_create(self.h, int(rank), int(world), C.cast(buf, C.c_void_p)), "nqmc_comm_create")
+        return buf.raw
+
+    def comm_attach(self, handles) -> None:
+        """Map the peers' inboxes; ``handles`` = one ``comm_create`` result per rank, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self.lib.nqmc_comm_attach(self.h, C.cast(buf, C.c_void_p)), "nqmc_comm_attach")
+
+    def comm_allreduce(self, vec) -> None:
+        """In-place sum over ranks of a float64 device tensor (len <= max(param_count, 8))."""
+        self._check(self.lib.nqmc_comm_allreduce(self.h, vec.data_ptr(), vec.numel(), self.stream), "nqmc_comm_allreduce")
 
     def use_tensor_cores(self, enable: bool):
         self._check(self.lib.nqmc_use_tensor_cores(self.h, int(enable)), "nqmc_use_tensor_cores")

@@ -41,6 +41,23 @@ def all_reduce_sum_(t):
     return t
 
 
+def attach_peer_memory(ctx) -> bool:
+    """Give ``ctx`` (a native ``Context``) the peer-memory communicator: afterwards ``ctx.walker_step`` /
+    ``walker_step_host`` sum ``hdr`` and ``gsum`` over all ranks in-stream with a one-shot all-reduce over NVLink
+    (csrc/nqmc_comm.cu) instead of two NCCL calls.  The handles travel through ``torch.distributed``.
+    Returns False (and leaves ``ctx`` rank-local) for a single process or a world larger than one node's 8 GPUs."""
+    rank, ws = world()
+    if ws <= 1 or ws > 8:
+        return False
+    import torch.distributed as dist
+    mine = ctx.comm_create(rank, ws)
+    handles = [None] * ws
+    dist.all_gather_object(handles, mine)
+    ctx.comm_attach(handles)
+    dist.barrier()
+    return True
+
+
 def combine_gradient(hdr, gsum):
     """gradient = 2 * sum_w (E_w - mean) O_w / n   (vmc.py:126-133) from all-reduced sums.
     Returns (grad, mean_energy, energy_std) with energy_std = std(ddof=0)/sqrt(n) (vmc.py:114)."""
