@@ -7,9 +7,10 @@
 // latency-bound (64 B and ~160 KB), so instead of two NCCL launches the step runs a one-shot all-reduce
 // over peer memory: every rank PUSHES its vector into an inbox slot on every peer (plain stores through
 // NVLink) and sums its own inbox in rank order -- so the result is bitwise identical on all ranks and
-// independent of arrival order.  The push is flag-in-data ("low latency" protocol): each 8-byte store carries
-// 4 bytes of payload and a 4-byte epoch tag, and an aligned 8-byte store is single-copy atomic, so the
-// receiver polls the payload words themselves; no fence, no separate flag, one NVLink traversal.
+// independent of arrival order.  The push is flag-in-data ("low latency" protocol): each 8-byte word carries
+// 4 bytes of payload and a 4-byte epoch tag, and an aligned 8-byte access is single-copy atomic (a 16-byte
+// vector access is two such words, each validated by its own tag), so the receiver polls the payload words
+// themselves; no fence, no separate flag, one NVLink traversal.
 //
 //   buffer on each rank (cudaMalloc, exported with cudaIpcGetMemHandle):
 //     inbox[2 parity][world][2 len_max]  uint64 = (tag << 32) | half of a double
@@ -23,7 +24,7 @@
 namespace {
 
 constexpr int MAX_WORLD = NQ_COMM_MAX_WORLD;
-constexpr int MAX_CTA = 32;
+constexpr int MAX_CTA = 128;
 
 struct CommDev {
   unsigned long long* inbox[MAX_WORLD];  // inboxes of all ranks (own one included)
@@ -31,43 +32,44 @@ struct CommDev {
   int64_t len_max;
 };
 
-__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void ld_sys_v2u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-// CTA c owns the slice [len c / n, len (c+1) / n) on every rank, so no grid-wide synchronisation is needed.
+// One element per thread; CTA c owns elements [256 c, 256 c + 256) on every rank, so no grid-wide synchronisation
+// is needed.  All loads of a poll round are independent (one L2 latency per round, not one per word).
 __global__ void __launch_bounds__(256) allreduce_f64_kernel(double* __restrict__ vec, const int64_t len, const CommDev c,
                                                             const unsigned long long epoch) {
-  const int tid = threadIdx.x, cta = blockIdx.x;
   const int par = (int)(epoch & 1ull);
   const unsigned long long tag = ((epoch + 1ull) & 0xffffffffull) << 32;
-  const int64_t lo = len * cta / gridDim.x, hi = len * (cta + 1) / gridDim.x;
-  // push: two tagged words per double into slot `rank` of every inbox
-  for (int64_t i = lo + tid; i < hi; i += blockDim.x) {
+  constexpr unsigned long long HI = 0xffffffff00000000ull, LO = 0xffffffffull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    // push: two tagged words per double into slot `rank` of every inbox
     const unsigned long long bits = (unsigned long long)__double_as_longlong(vec[i]);
-    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
-    for (int q = 0; q < c.world; ++q) {
-      unsigned long long* dst = c.inbox[q] + (((int64_t)par * c.world + c.rank) * c.len_max + i) * 2;
-      st_sys_u64(dst, w0);
-      st_sys_u64(dst + 1, w1);
-    }
-  }
-  // pull: poll the own inbox until every word of the slice carries this epoch's tag; sum in rank order
-  const unsigned long long* in = c.inbox[c.rank] + (int64_t)par * c.world * c.len_max * 2;
-  for (int64_t i = lo + tid; i < hi; i += blockDim.x) {
+    const unsigned long long w0 = tag | (bits & LO), w1 = tag | (bits >> 32);
+#pragma unroll
+    for (int q = 0; q < MAX_WORLD; ++q)
+      if (q < c.world) {
+        unsigned long long* dst = c.inbox[q] + (((int64_t)par * c.world + c.rank) * c.len_max + i) * 2;
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+      }
+    // pull: poll the own inbox until both words of every rank carry this epoch's tag; sum in rank order
+    const unsigned long long* in = c.inbox[c.rank] + ((int64_t)par * c.world * c.len_max + i) * 2;
+    unsigned long long a[MAX_WORLD], b[MAX_WORLD];
+    bool all;
+    do {
+      all = true;
+#pragma unroll
+      for (int q = 0; q < MAX_WORLD; ++q)
+        if (q < c.world) ld_sys_v2u64(in + (int64_t)q * c.len_max * 2, a[q], b[q]);
+#pragma unroll
+      for (int q = 0; q < MAX_WORLD; ++q)
+        if (q < c.world) all = all && (a[q] & HI) == tag && (b[q] & HI) == tag;
+    } while (!all);
     double s = 0.0;
-    for (int q = 0; q < c.world; ++q) {
-      const unsigned long long* src = in + ((int64_t)q * c.len_max + i) * 2;
-      unsigned long long w0, w1;
-      do { w0 = ld_sys_u64(src); } while ((w0 & 0xffffffff00000000ull) != tag);
-      do { w1 = ld_sys_u64(src + 1); } while ((w1 & 0xffffffff00000000ull) != tag);
-      s += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-    }
+#pragma unroll
+    for (int q = 0; q < MAX_WORLD; ++q)
+      if (q < c.world) s += __longlong_as_double((long long)((a[q] & LO) | (b[q] << 32)));
     vec[i] = s;
   }
 }
@@ -146,7 +148,7 @@ int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st) 
   d.rank = c->rank;
   d.world = c->world;
   d.len_max = c->len_max;
-  int n_cta = (int)((len + 1023) / 1024);
+  int n_cta = (int)((len + 255) / 256);
   if (n_cta > MAX_CTA) n_cta = MAX_CTA;
   allreduce_f64_kernel<<<n_cta, 256, 0, st>>>(vec, len, d, c->epoch);
   c->epoch++;
