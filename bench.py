@@ -208,6 +208,27 @@ def run_ours(args):
     total_ms = float(t.item())
     h = hdr.cpu().numpy()
 
+    # ---- SURVEY 8(d) secondary figure: the reference's inter-iteration burn-in (vmc.py:247, n_burn=10 value-only MH
+    # steps before every sampled step), counting only the sampled steps
+    def burn10_iter(k):
+        for j in range(10):
+            ctx.mh_step(r, logp, SIGMA, seed=SEED + 1, step=(1 << 23) + 10 * k + j, walker_id0=lo)
+        one_step()
+    nb = max(args.steps // 5, 4)
+    for k in range(2):
+        burn10_iter(k)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for k in range(nb):
+        burn10_iter(2 + k)
+    b1.record()
+    barrier()
+    tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    burn10_value = world * Wl * nb / (float(tb.item()) * 1e-3)
+
     # ---- e2e: host buffers in pinned memory, copies inside the timed region -----------------------
     nn = 3 * mol.n_electrons
     r_host = torch.empty((Wl, mol.n_electrons, 3), dtype=torch.float32).pin_memory()
@@ -279,12 +300,15 @@ def run_ours(args):
                        "collective": ("none" if world == 1 else "peer-memory one-shot all-reduce inside nqmc_walker_step (NVLink)"
                                       if peer else "NCCL all_reduce x2"),
                        "algorithmic_flop_per_walker_step": flops_step},
+            "with_burn10": {"value": burn10_value, "unit": "sampled walker-steps/s",
+                            "note": "10 value-only MH steps before every sampled step (reference n_burn between iterations, "
+                                    "vmc.py:247); only sampled steps counted; L2 not flushed"},
             "clocks": clocks,
             "e2e": {"value": world * Wl * args.steps / e2e_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if (world == 1 or peer)
                     else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host"},
             "gpu_launches": launches,
-            "roofline": ({"bound": "tensor", "kernel": "orb_eval5_tc_kernel (orbital forward value+grad+Laplacian; H x H layer = tcgen05 3xTF32, input layer = FFMA)",
+            "roofline": ({"bound": "tensor", "kernel": "orb_lap_pc_kernel<4> (orbital forward value+grad+Laplacian; H x H layer = tcgen05 3xTF32 with A in TMEM, input layer = FFMA)",
                           "achieved": ach, "peak": peak3, "unit": "TFLOP/s", "frac": (ach / peak3) if ach else None,
                           "peak_source": "cuBLAS TF32 GEMM 8192^3 measured live in this run, divided by 3 (3xTF32 split); "
                                          "MEASURED_PEAKS.json has only a bf16 figure",

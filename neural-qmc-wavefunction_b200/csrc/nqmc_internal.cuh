@@ -196,6 +196,29 @@ int nq_simple_logpsi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, cu
 int nq_simple_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
 int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                     int64_t W, double* out, cudaStream_t st);
+// Programmatic dependent launch (PDL): a kernel launched through nq_launch_pdl may become resident while its
+// predecessor in the stream is still draining (once every CTA of the predecessor has called nq_pdl_trigger or
+// exited); it must call nq_pdl_wait() before touching anything a predecessor wrote.  Used so that the per-CTA weight
+// staging of the tensor-core kernels (reads theta only) overlaps the small kernel in front of them.
+template <typename... KArgs, typename... Args>
+inline cudaError_t nq_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void nq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void nq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // peer-memory communicator (nqmc_comm.cu)
 int nq_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out);
 int nq_comm_attach(nqmc_ctx* ctx, const void* handles);

@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(TCT, 1)
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_u = smem_u32(&bars[0]), bar_d = smem_u32(&bars[1]), bar_g2 = smem_u32(&bars[2]), bar_g = smem_u32(&bars[3]);
   uint32_t ph_u = 0, ph_d = 0, ph_g2 = 0, ph_g = 0;
+  nq_pdl_wait();                              // everything above read theta only; header, E_L, inverses come from predecessors
   float centerf = 0.f;
   if (hdr != nullptr) centerf = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
 
@@ -581,8 +582,12 @@ int launch_t(nqmc_ctx* ctx, const SmemMap& mp, const float* r, const float* wgt,
   }
   {
     ProfScope ps(ctx, NQ_PROF_BWD, st);
-    orb_bwd_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
-                                                                     n_chunks, ctx->p_mlp);
+    if (ctx->prof_on)
+      orb_bwd_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
+                                                                       n_chunks, ctx->p_mlp);
+    else
+      NQMC_CUDA(nq_launch_pdl(orb_bwd_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), (size_t)mp.total, st, s, ctx->theta, r,
+                              ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp, n_chunks, ctx->p_mlp));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(TCT, 1)
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
+  nq_pdl_wait();                              // everything above read theta only; the positions come from the predecessor
 
   if (!worker) {
     // =============================== MMA issuer warp =====================================================
@@ -348,7 +349,8 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t 
   if (n_chunks > max_items) n_chunks = (int)max_items;
   {
     ProfScope ps(ctx, NQ_PROF_EVAL5, st);
-    orb_lap_pc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    if (ctx->prof_on) orb_lap_pc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    else NQMC_CUDA(nq_launch_pdl(orb_lap_pc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(TCT, 1)
     __syncwarp();
   };
 
+  nq_pdl_wait();                              // everything above read theta only; the positions come from the predecessor
   // ---- software pipeline, depth 2 -------------------------------------------------------------------------------
   int b = 0;
   if (chunk < n_items) {
@@ -285,7 +286,8 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, int n_chunks,
   }
   {
     ProfScope ps(ctx, NQ_PROF_EVAL1, st);
-    orb_eval1_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    if (ctx->prof_on) orb_eval1_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    else NQMC_CUDA(nq_launch_pdl(orb_eval1_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

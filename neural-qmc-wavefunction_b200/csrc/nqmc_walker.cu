@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(WT) assemble_stats_kernel(const DevSys s, cons
 // hdr[0..4] and jas[0..7] from the block partials (one warp per slot, fixed order => deterministic)
 __global__ void stats13_finish_kernel(const double* __restrict__ part, const int nblk, double* __restrict__ hdr,
                                       double* __restrict__ jas) {
+  nq_pdl_trigger();                                    // the reverse pass behind this kernel may start staging its weights
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double a = 0;
   if (slot < 13)
@@ -364,6 +365,7 @@ __global__ void jastrow_from_sums_kernel(const DevSys s, const double* __restric
 __global__ void propose_kernel(const DevSys s, const float* __restrict__ r, const float* __restrict__ normals,
                                const uint64_t seed, const uint64_t step, const int64_t wid0, const float sigma,
                                const int64_t W, float* __restrict__ r_prop) {
+  nq_pdl_trigger();                                    // the value pass behind this kernel may start staging its weights
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   const int nn = 3 * s.N;
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(WT) accept_kernel(const DevSys s, const float*
                                                     const uint64_t seed, const uint64_t step, const int64_t wid0,
                                                     const int64_t W, uint8_t* __restrict__ accept,
                                                     float* __restrict__ n_acc, float* __restrict__ acc_flag) {
+  nq_pdl_trigger();                                    // the 5-channel pass behind this kernel may start staging its weights
   const int64_t w = (int64_t)blockIdx.x * WT + threadIdx.x;
   if (w >= W) return;
   float la, sg, T, ven, vee;
