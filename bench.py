@@ -313,6 +313,9 @@ def run_ours(args):
                           "peak_source": "cuBLAS TF32 GEMM 8192^3 measured live in this run, divided by 3 (3xTF32 split); "
                                          "MEASURED_PEAKS.json has only a bf16 figure",
                           "tf32_dense_tflops_measured": tf32_peak,
+                          "traffic": 3.2566e6, "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum "
+                          "from the ncu --set full capture in profiles/r1c_ncu_full_metrics.txt (3.26 MB read = the walker positions, "
+                          "0 written: the 10.5 MB of orbital channels stay in the 126 MB L2 for the next kernel)",
                           "frac_of_mixed_floor": (t_floor / (ms5 / max(n5, 1) * 1e-3)) if n5 else None,
                           "mixed_floor_note": "floor = HxH-layer flops / (tf32/3) + other-layer flops / measured FFMA peak",
                           "frac_vs_bf16_peak": (ach / pk["bf16_tflops"]) if (ach and pk.get("bf16_tflops")) else None}
@@ -322,7 +325,7 @@ def run_ours(args):
                           "peak_source": "measured live: nqmc_ffma_peak (register FFMA chains)"}),
             "roofline_context": {"ffma_peak_tflops_measured": ffma_peak, "peak_nominal_148x128x2x1.965GHz": 74.4,
                          "bf16_tensor_peak_measured": pk.get("bf16_tflops"),
-                         "hbm_gbs_measured": pk.get("hbm_gbs"), "traffic": None,
+                         "hbm_gbs_measured": pk.get("hbm_gbs"),
                          "whole_step_achieved_tflops": flops_step * Wl / (total_ms / args.steps * 1e-3) / 1e12,
                          "kernel_ms": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
                          "kernel_launches": {k: v[1] for k, v in prof.items()}},
