@@ -7,18 +7,23 @@
 //     U2 = h1 W2                                UMMA  M=128 rows, N=64, K=64    A: h1 in TENSOR MEMORY, B: W2 smem
 //     h2 = tanh(U2 + b2); dW3 += seed h2; delta2 = seed W3 (1-h2^2)
 //     D1 = delta2 W2^T                          UMMA  M=128 rows, N=64, K=64    A: delta2 in TMEM,      B: W2^T smem
-//     G2 += [h1 | 1]^T delta2                   UMMA  M=128 (64 units + ones -> db2), N=64, K=128 rows  (smem x smem)
+//     G2 += h1^T delta2                         UMMA  M=128 (64 units used), N=64, K=128 rows          (smem x smem)
+//     GB += delta2^T [f | 1]                    UMMA  M=128 (64 units used), N=16, K=128 rows: ones column -> db2
 //     delta1 = D1 (1-h1^2)
-//     G1 += [f | 1]^T delta1                    UMMA  M=128 (F features + ones -> db1), N=64, K=128 rows (smem x smem)
-// G2 / G1 accumulate in tensor memory for the whole kernel and are read back once.
+//     G1^T += delta1^T [f | 1]                  UMMA  M=128 (64 units used), N=16, K=128 rows: dW1^T, ones column -> db1
+// G2 / GB / G1^T accumulate in tensor memory for the whole kernel and are read back once.
 //
-// Operand layouts.  tf32 operands may only be MN-major in a special swizzled format, so every shared-memory
-// operand here is K-major, no swizzle: element (mn, k) at (k/4)*LBO + mn*16 + (k%4)*4 bytes, SBO = 128.
+// Operand layouts.
 //   * "row" operands of U2 / D1 (A[m=row][k=unit]) are written by their owning thread straight into TMEM
-//     (tcgen05.st, lane = row): no shared-memory traffic at all for them.
-//   * "K = row" operands of G2 / G1 need 4 consecutive rows of one unit in a 16-byte granule: a thread owns
-//     one row, so the 4 lanes of a quad transpose their 4x4 blocks with two butterfly shuffle stages
-//     (4 SHFL per block) before the hi/lo split; features go through a small [feature][row] staging array.
+//     (tcgen05.st, lane = row): no shared-memory traffic at all for them.  B = W2 / W2^T: K-major, no swizzle,
+//     element (n, k) at (k/4)*LBO + n*16 + (k%4)*4 bytes, SBO = 128.
+//   * "K = row" operands (h1, delta2, delta1 as [unit][row]): a thread owns one ROW, i.e. one k, and 16 consecutive
+//     units, so they are MN-major.  tf32 accepts MN-major only with SWIZZLE_128B_BASE32B (layout type 1; with
+//     SWIZZLE_NONE the accumulator silently stays zero).  The hardware's layout was probed
+//     (scripts/exp/mn_major_probe.cu): atoms of 4 rows x 128 bytes, the 32-byte chunk index inside a row XORed with
+//     row % 4.  The owning thread therefore stores two 32-byte chunks per buffer straight from registers: no
+//     transposition, no shuffles (the previous version spent a third of its instructions on 4x4 quad transposes).
+//   * the feature operand [f|1] (N = 16) stays K-major and goes through a small [feature][row] staging array.
 #include <cstdlib>
 
 #include "nqmc_internal.cuh"
@@ -28,49 +33,58 @@ namespace {
 constexpr int H = 64;
 constexpr int NQ = 4;                 // threads per row
 constexpr int TCW = 128 * NQ;         // worker threads
-constexpr int TCT = TCW;              // 16 warps -> 128 registers per thread (a 17th warp would cap them at 96 and spill)
-constexpr int ISSUER = TCW / 32 - 1;  // the last worker warp also issues the MMAs (one elected lane, predicated)
+// 16 worker warps + one warpgroup holding the MMA issuer warp and three warps that only take part in the register
+// split.  20 warps get 96 registers each at launch (61,440 in the CTA's pool); setmaxnreg then moves the issuer
+// warpgroup to 32 and the four worker warpgroups to 112 -- the pool is per CTA, so 512 x 112 + 128 x 32 must not
+// exceed what was allotted at launch (asking for more blocks forever).  Alternatives measured: a plain 17-warp CTA
+// caps every thread at 96 (spills); 16 warps with the issue duty folded into a worker warp stall that warp on the
+// UMMA queue and everybody else on the next barrier.  setmaxnreg needs whole warpgroups and one register budget per
+// code path, hence the role split.
+constexpr int TCT = TCW + 128;
+constexpr int ISSUER = TCW / 32;      // warp 16
+constexpr int NSYNC = TCT;            // threads meeting at the tile barriers: workers + the four issuer warps
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G2 = 128, C_G1 = 192, C_AH = 256, C_AL = 320;
-// Row-group strides of the transposed buffers.  A quarter warp (rows 4g..4g+7, 8 lanes x 16 B) stores to two
-// consecutive row groups, so the stride has to be 64 (mod 128) bytes for the two halves to land in disjoint banks.
-constexpr int RGH_MIN = (H + 1) * 16; // 64 units + the ones unit = 1040 B (unpadded: 2-way store conflicts)
-constexpr int RG_PAD = (H + 4) * 16;  // 1088 B = 64 (mod 128)
+constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G2 = 128, C_G1 = 192, C_GB = 224, C_AH = 256, C_AL = 320;
+// K = rows operands of the weight-gradient GEMMs (h1, delta2, delta1): MN-major, SWIZZLE_128B_BASE32B.  Layout as
+// probed on B200 (scripts/exp/mn_major_probe.cu; tf32 MN-major with SWIZZLE_NONE silently yields zeros):
+//   byte(unit, row) = (unit/32) LBO + (row/4) SBO + (row%4) 128 + (((unit%32)/8) ^ (row%4)) 32 + (unit%8) 4
+// i.e. a thread that owns 16 consecutive units of its row stores two 32-byte chunks straight from registers -- no
+// transposition in software.  SBO must stay 512 (a padded SBO faults as misaligned), so the two row groups a
+// quarter warp touches share banks (2-way conflict on these stores).
+constexpr int MN_SBO = 512;                 // 4 rows x 128 bytes
+constexpr int MN_LBO = (128 / 4) * MN_SBO;  // one atom column: 32 units x 128 rows = 16 KB
+constexpr int MN_BUF = (H / 32) * MN_LBO;   // 64 units: 32 KB per hi / lo buffer
 constexpr int FS_LD = 128 + 4;        // leading dimension of the [feature][row] staging array (float4 reads, stride 4 banks)
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NRG = ROWS / 4;         // 32 row groups (granule = 4 consecutive rows of one unit)
 constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                                                   = 16384 B
 
 struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
-  int hT_hi, hT_lo, dT_hi, dT_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
-  int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the feature buffer
-  int n_g1;
-  int rgh, rgd;       // row-group strides of the transposed h1 / delta buffers
+  int hM_hi, hM_lo, dM_hi, dM_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
+  int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the (K-major) feature buffer
+  int n_g1;           // N of the [f|1] MMAs (a multiple of 8): columns >= n_fu read into the next row group, ignored
 };
-__host__ __device__ inline SmemMap make_map(int F, bool pad_h = true) {
+__host__ __device__ inline SmemMap make_map(int F) {
   SmemMap m;
   m.n_fu = 4 * ((F + 1 + 3) / 4);
-  m.n_g1 = 8 * ((F + 1 + 7) / 8);   // N of the G1^T MMAs (a multiple of 8): columns >= n_fu read into the next row group, ignored
+  m.n_g1 = 8 * ((F + 1 + 7) / 8);
   m.rgf = m.n_fu * 16;
-  m.rgd = RG_PAD;
-  m.rgh = pad_h ? RG_PAD : RGH_MIN;
   int o = 0;
-  m.fT_hi = o; o += NRG * m.rgf;
-  m.fT_lo = o; o += NRG * m.rgf;
-  m.hT_hi = o; o += NRG * m.rgh;
-  m.hT_lo = o; o += NRG * m.rgh;
-  m.dT_hi = o; o += NRG * m.rgd;
-  m.dT_lo = o; o += NRG * m.rgd;
+  m.hM_hi = o; o += MN_BUF;
+  m.hM_lo = o; o += MN_BUF;
+  m.dM_hi = o; o += MN_BUF;
+  m.dM_lo = o; o += MN_BUF;
   m.wa_hi = o; o += WB;
   m.wa_lo = o; o += WB;
   m.wb_hi = o; o += WB;
   m.wb_lo = o; o += WB;
+  m.fT_hi = o; o += NRG * m.rgf;
+  m.fT_lo = o; o += NRG * m.rgf;
   m.fstage = o; o += m.n_fu * FS_LD * 4;
   m.misc = o; o += (F * H + 3 * H + H + 8) * 4 + 64;
   m.total = o;
-  if (pad_h && m.total > SMEM_LIMIT) return make_map(F, false);   // many nuclei: give up the h1 padding to fit
   return m;
 }
 
@@ -78,8 +92,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {   // MN-major, SWIZZLE_128B_BASE32B (layout type 1)
+  return umma_desc(smem_addr, MN_LBO, MN_SBO) | (1ull << 61);
+}
 // D=f32, A=B=tf32, both K-major, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+// G2: A and B MN-major, M = 64 (the 64 h1 units; half the A-operand traffic of M = 128, same UMMA time).
+// An M = 64 accumulator row u lives in TMEM lane (u / 16) * 32 + u % 16 (probed: scripts/exp/m64_probe.cu).
+constexpr uint32_t IDESC_MN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,6 +120,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory"); }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -168,30 +189,23 @@ __device__ __forceinline__ void stage_rows_tmem(uint32_t t_hi, uint32_t t_lo, co
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// 4x4 transpose across the 4 lanes of a quad (two butterfly stages), then hi/lo split and one 16-byte store per
-// unit: on return the granule (rows row0..row0+3 of unit c0 + 4u + (lane & 3)) is in the transposed buffers.
-__device__ __forceinline__ void stage_cols_smem(uint8_t* hi_rg, uint8_t* lo_rg, const int c0, const int t,
-                                                const float (&v)[16]) {
-  const bool odd = t & 1, upper = t & 2;
+// 16 values of this thread's row (units c0 .. c0+15) -> tf32 hi / lo in an MN-major swizzled operand buffer:
+// two 32-byte chunks per buffer at byte offsets off0 / off1 (see the layout formula above), straight from registers
+__device__ __forceinline__ void stage_mn(uint8_t* hi, uint8_t* lo, const int off0, const int off1, const float (&v)[16]) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float x0 = v[4 * u], x1 = v[4 * u + 1], x2 = v[4 * u + 2], x3 = v[4 * u + 3];
-    // stage 1 (partner t^1): 2x2 blocks
-    const float s0 = odd ? x0 : x1, s1 = odd ? x2 : x3;
-    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    const float y0 = odd ? r0 : x0, y1 = odd ? x1 : r0, y2 = odd ? r1 : x2, y3 = odd ? x3 : r1;
-    // stage 2 (partner t^2): swap the off-diagonal 2-element blocks
-    const float q0 = upper ? y0 : y2, q1 = upper ? y1 : y3;
-    const float p0 = __shfl_xor_sync(0xffffffffu, q0, 2), p1 = __shfl_xor_sync(0xffffffffu, q1, 2);
-    const float z0 = upper ? p0 : y0, z1 = upper ? p1 : y1, z2 = upper ? y2 : p0, z3 = upper ? y3 : p1;
-    float4 h4, l4;
-    split_tf32(z0, h4.x, l4.x);
-    split_tf32(z1, h4.y, l4.y);
-    split_tf32(z2, h4.z, l4.z);
-    split_tf32(z3, h4.w, l4.w);
-    const int unit = c0 + 4 * u + t;
-    *reinterpret_cast<float4*>(hi_rg + unit * 16) = h4;
-    *reinterpret_cast<float4*>(lo_rg + unit * 16) = l4;
+  for (int c = 0; c < 2; ++c) {
+    uint8_t* ph = hi + (c == 0 ? off0 : off1);
+    uint8_t* pl = lo + (c == 0 ? off0 : off1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 h4, l4;
+      split_tf32(v[8 * c + 4 * h + 0], h4.x, l4.x);
+      split_tf32(v[8 * c + 4 * h + 1], h4.y, l4.y);
+      split_tf32(v[8 * c + 4 * h + 2], h4.z, l4.z);
+      split_tf32(v[8 * c + 4 * h + 3], h4.w, l4.w);
+      *reinterpret_cast<float4*>(ph + 16 * h) = h4;
+      *reinterpret_cast<float4*>(pl + 16 * h) = l4;
+    }
   }
 }
 
@@ -227,6 +241,8 @@ __global__ void __launch_bounds__(TCT, 1)
 
   // ---- setup ----------------------------------------------------------------------------------------------
   for (int idx = tid; idx < mp.wa_hi / 16; idx += TCT) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = tid; idx < (mp.fstage - mp.fT_hi) / 16; idx += TCT)
+    reinterpret_cast<float4*>(smem + mp.fT_hi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int idx = tid; idx < mp.n_fu * FS_LD; idx += TCT) fstage[idx] = 0.f;
   for (int idx = tid; idx < F * H; idx += TCT) W1s[idx] = theta[off.W1 + idx];
   for (int q = tid; q < H; q += TCT) {
@@ -237,14 +253,15 @@ __global__ void __launch_bounds__(TCT, 1)
   for (int q = tid; q < H + 8; q += TCT) redS[q] = 0.f;
   {
     // all loads of a thread in flight at once: with a cold L2 each dependent round trip costs ~1 us
-    constexpr int NL = H * H / TCT;
-    static_assert(NL * TCT == H * H, "W2 staging assumes the block size divides H*H");
+    constexpr int NL = H * H / TCW;
+    static_assert(NL * TCW == H * H, "W2 staging assumes the worker count divides H*H");
     float wv[NL];
 #pragma unroll
-    for (int i = 0; i < NL; ++i) wv[i] = theta[off.W2 + tid + i * TCT];
+    for (int i = 0; i < NL; ++i) wv[i] = worker ? theta[off.W2 + tid + i * TCW] : 0.f;
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
-      const int idx = tid + i * TCT;
+      if (!worker) break;
+      const int idx = tid + i * TCW;
       const int k = idx / H, j = idx % H;
       float hi, lo;
       split_tf32(wv[i], hi, lo);
@@ -259,10 +276,8 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   __syncthreads();
-  // the ones unit (index 64) of the transposed h1 buffer -> row 64 of G2 = db2 ; hi = 1, lo stays 0
-  for (int g = tid; g < NRG; g += TCT) *reinterpret_cast<float4*>(smem + mp.hT_hi + g * mp.rgh + H * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
   if (tid == 0) {
-    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
+    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(b == 2 ? 2 : 1));   // bar_g2: G2 and GB issuers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -287,17 +302,20 @@ __global__ void __launch_bounds__(TCT, 1)
   for (int j = 0; j < UPT; ++j) gW3[j] = 0.f;
   float gb3 = 0.f;
   const int c0 = UPT * quarter;                     // first hidden unit / output column of this thread
-  const int t4 = tid & 3;                           // position inside the lane quad == row % 4
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  uint8_t* hT_hi = smem + mp.hT_hi + (row >> 2) * mp.rgh;
-  uint8_t* hT_lo = smem + mp.hT_lo + (row >> 2) * mp.rgh;
-  uint8_t* dT_hi = smem + mp.dT_hi + (row >> 2) * mp.rgd;
-  uint8_t* dT_lo = smem + mp.dT_lo + (row >> 2) * mp.rgd;
+  // byte offsets of this thread's two 32-byte chunks (units c0..c0+7, c0+8..c0+15 of its row) in an MN-major buffer
+  const int mn_row = (quarter >> 1) * MN_LBO + (row >> 2) * MN_SBO + (row & 3) * 128, mn_cb = 2 * (quarter & 1);
+  const int mn_off0 = mn_row + ((mn_cb ^ (row & 3)) << 5), mn_off1 = mn_row + (((mn_cb + 1) ^ (row & 3)) << 5);
+  uint8_t* hM_hi = smem + mp.hM_hi;
+  uint8_t* hM_lo = smem + mp.hM_lo;
+  uint8_t* dM_hi = smem + mp.dM_hi;
+  uint8_t* dM_lo = smem + mp.dM_lo;
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
-  // G1^T: D=f32, A=B=tf32, K-major, M=128 (64 delta1 units + 64 ignored rows), N = n_fu
-  const uint32_t idesc_g1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(mp.n_g1 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+  // [f|1] products: D=f32, A=B=tf32, A MN-major (delta), B K-major (features), M = 64 delta units, N = n_g1
+  const uint32_t idesc_g1 =
+      (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(mp.n_g1 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
   // positions and reverse seed of one tile row; the next tile's are fetched while the current one computes
   float nx = 0.f, ny = 0.f, nz = 0.f, nwt = 1.f, ninv = 0.f;     // raw loads; consumed one tile later
   auto fetch = [&](const int64_t item) {
@@ -315,26 +333,99 @@ __global__ void __launch_bounds__(TCT, 1)
   if (worker && chunk < n_items) fetch(chunk);
   // Pipeline (one tile = 3 CTA barriers; delta1 of tile t stays in registers until tile t+1's first phase, so the
   // wait for G2(t) -- which still reads the buffer delta1^T goes into -- hides behind layer 1 of tile t+1):
-  //   P1  layer 1(t) -> A(h1) in TMEM ; delta1^T(t-1) -> dT                 | issue U2(t), G1(t-1)
-  //   P2  h1^T(t) -> hT ; wait U2 ; h2, dW3, delta2 -> A(delta2) in TMEM      | issue D1(t)
-  //   P3  wait G1(t-1) ; delta2^T(t) -> dT ; features(t) -> fT              | issue G2(t)
+  //   P1  layer 1(t) -> A(h1) in TMEM ; delta1(t-1) -> dM                   | issue U2(t), G1^T(t-1) = delta1^T [f|1]
+  //   P2  h1(t) -> hM ; wait U2 ; h2, dW3, delta2 -> A(delta2) in TMEM        | issue D1(t)
+  //   P3  wait G1^T(t-1) ; delta2(t) -> dM ; features(t) -> fT              | issue G2(t) = h1^T delta2, GB(t) = delta2^T [f|1]
   //   P4  wait D1 ; delta1(t) = D1 (1 - h1^2)  (registers)
+  // The ones column of [f|1] yields db1 (from G1^T) and db2 (from GB).
   float d1[UPT];
 #pragma unroll
   for (int j = 0; j < UPT; ++j) d1[j] = 0.f;
-  auto issue_g1 = [&](const uint32_t leader, const bool first) {   // G1^T += delta1 [f|1]  (M = delta1 unit, N = feature)
-    const uint64_t ah = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), al = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
+  // dst += (delta in dM)^T [f|1]   (M = delta unit, N = feature; 48 UMMAs of N = n_g1: 8 cycles each)
+  auto issue_df = [&](const uint32_t dst, const uint32_t leader, const bool first) {
+    const uint64_t ah = umma_desc_mn(sbase + mp.dM_hi), al = umma_desc_mn(sbase + mp.dM_lo);
     const uint64_t bh = umma_desc(sbase + mp.fT_hi, mp.rgf, 128), bl = umma_desc(sbase + mp.fT_lo, mp.rgf, 128);
-#pragma unroll
-    for (int ks = 0; ks < ROWS / 8; ++ks) {
-      const uint64_t ao = (uint64_t)((ks * 2 * mp.rgd) >> 4), bo = (uint64_t)((ks * 2 * mp.rgf) >> 4);
+    const uint64_t da = (uint64_t)((2 * MN_SBO) >> 4), db = (uint64_t)((2 * mp.rgf) >> 4);
+    uint64_t ao = 0, bo = 0;
+#pragma unroll 1
+    for (int ks = 0; ks < ROWS / 8; ++ks, ao += da, bo += db) {   // not unrolled: the issuer warp lives on 32 registers
       const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-      umma_ss(tmem_base + C_G1, ah + ao, bh + bo, idesc_g1, acc, leader);
-      umma_ss(tmem_base + C_G1, al + ao, bh + bo, idesc_g1, 1u, leader);
-      umma_ss(tmem_base + C_G1, ah + ao, bl + bo, idesc_g1, 1u, leader);
+      umma_ss(tmem_base + dst, ah + ao, bh + bo, idesc_g1, acc, leader);
+      umma_ss(tmem_base + dst, al + ao, bh + bo, idesc_g1, 1u, leader);
+      umma_ss(tmem_base + dst, ah + ao, bl + bo, idesc_g1, 1u, leader);
     }
-    umma_commit(bar_g, leader);
   };
+  if (!worker) {
+    // =============================== issuer warpgroup ========================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    // The four warps of this warpgroup share the issue work (one thread sustains only about one tcgen05.mma per 100
+    // cycles, scripts/exp/mma_rate.cu): warp 0: U2, D1 (the critical chain) ; 1: G1^T ; 2: G2 ; 3: GB.
+    const int iw = warp - ISSUER;
+    const uint32_t leader = elect_one();
+    int64_t n_done = 0;
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
+      tile_barrier();                                    // P1 done: A(h1) in TMEM, delta1(t-1) in dM
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (iw == 0) {
+        const uint64_t bh = umma_desc(sbase + mp.wa_hi, H * 16, 128), bl = umma_desc(sbase + mp.wa_lo, H * 16, 128);
+#pragma unroll 1
+        for (int ks = 0; ks < H / 8; ++ks) {             // U2 = h1 W2 (A from tensor memory)
+          const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+          const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
+          umma_ts(tmem_base + C_U2, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+          umma_ts(tmem_base + C_U2, al, bh + bo, 1u, leader);
+          umma_ts(tmem_base + C_U2, ah, bl + bo, 1u, leader);
+        }
+        umma_commit(bar_u, leader);
+      } else if (iw == 1 && n_done > 0) {
+        issue_df(C_G1, leader, n_done == 1);             // G1^T(t-1) += delta1^T [f|1]
+        umma_commit(bar_g, leader);
+      }
+      tile_barrier();                                    // P2 done: A(delta2) in TMEM
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (iw == 0) {
+        const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
+#pragma unroll 1
+        for (int ks = 0; ks < H / 8; ++ks) {             // D1 = delta2 W2^T (A from tensor memory)
+          const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+          const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
+          umma_ts(tmem_base + C_D1, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+          umma_ts(tmem_base + C_D1, al, bh + bo, 1u, leader);
+          umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
+        }
+        umma_commit(bar_d, leader);
+      }
+      tile_barrier();                                    // P3 done: h1 in hM, delta2 in dM, features in fT
+      if (iw == 2) {
+        const uint64_t ah = umma_desc_mn(sbase + mp.hM_hi), al = umma_desc_mn(sbase + mp.hM_lo);
+        const uint64_t bh = umma_desc_mn(sbase + mp.dM_hi), bl = umma_desc_mn(sbase + mp.dM_lo);
+#pragma unroll 1
+        for (int ks = 0; ks < ROWS / 8; ++ks) {          // G2 += h1^T delta2   (both operands MN-major, K = 8 rows per UMMA)
+          const uint64_t ko = (uint64_t)((ks * 2 * MN_SBO) >> 4);
+          const uint32_t acc = (n_done == 0 && ks == 0) ? 0u : 1u;
+          umma_ss(tmem_base + C_G2, ah + ko, bh + ko, IDESC_MN, acc, leader);
+          umma_ss(tmem_base + C_G2, al + ko, bh + ko, IDESC_MN, 1u, leader);
+          umma_ss(tmem_base + C_G2, ah + ko, bl + ko, IDESC_MN, 1u, leader);
+        }
+        umma_commit(bar_g2, leader);
+      } else if (iw == 3) {
+        issue_df(C_GB, leader, n_done == 0);             // GB += delta2^T [f|1]: its ones column is db2
+        umma_commit(bar_g2, leader);
+      }
+    }
+    if (n_done > 0) {                                    // drain: G1^T of the last tile
+      tile_barrier();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (iw == 1) {
+        issue_df(C_G1, leader, n_done == 1);
+        umma_commit(bar_g, leader);
+      }
+    }
+    tile_barrier();                                      // workers have read every accumulator
+    return;
+  }
+  // =============================== worker warps ================================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
   int64_t n_done = 0;                                  // tiles this CTA has completed
   for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
     float h1[UPT], d2[UPT], seed = 0.f;
@@ -347,7 +438,6 @@ __global__ void __launch_bounds__(TCT, 1)
         seed = wt * ninv;
         if ((item / ns) * ROWS + row >= W || !isfinite(seed)) seed = 0.f;
       }
-      if (item + n_chunks < n_items) fetch(item + n_chunks);
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
       const float pc[3] = {x, y, z};
@@ -394,31 +484,15 @@ __global__ void __launch_bounds__(TCT, 1)
       if (n_done > 0) {
         mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
         ph_g2 ^= 1;
-        stage_cols_smem(dT_hi, dT_lo, c0, t4, d1);
+        stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == ISSUER) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t leader = elect_one();
-      const uint64_t bh = umma_desc(sbase + mp.wa_hi, H * 16, 128), bl = umma_desc(sbase + mp.wa_lo, H * 16, 128);
-#pragma unroll
-      for (int ks = 0; ks < H / 8; ++ks) {               // U2 = h1 W2 (A from tensor memory)
-        const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
-        const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
-        umma_ts(tmem_base + C_U2, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
-        umma_ts(tmem_base + C_U2, al, bh + bo, 1u, leader);
-        umma_ts(tmem_base + C_U2, ah, bl + bo, 1u, leader);
-      }
-      umma_commit(bar_u, leader);
-      if (n_done > 0) issue_g1(leader, n_done == 1);
-      __syncwarp();
-    }
+    tile_barrier();
     // ======== P2 ========
     if (worker) {
-      stage_cols_smem(hT_hi, hT_lo, c0, t4, h1);         // G2(t-1), the reader of this buffer, was waited for in P1
+      stage_mn(hM_hi, hM_lo, mn_off0, mn_off1, h1);         // G2(t-1), the reader of this buffer, was waited for in P1
       mbar_wait(bar_u, ph_u);
       ph_u ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -436,26 +510,12 @@ __global__ void __launch_bounds__(TCT, 1)
       for (int j = 0; j < UPT; ++j) d2[j] = v[j];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == ISSUER) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t leader = elect_one();
-      const uint64_t bh = umma_desc(sbase + mp.wb_hi, H * 16, 128), bl = umma_desc(sbase + mp.wb_lo, H * 16, 128);
-#pragma unroll
-      for (int ks = 0; ks < H / 8; ++ks) {               // D1 = delta2 W2^T (A from tensor memory)
-        const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
-        const uint32_t ah = tmem_base + C_AH + 8 * ks, al = tmem_base + C_AL + 8 * ks;
-        umma_ts(tmem_base + C_D1, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
-        umma_ts(tmem_base + C_D1, al, bh + bo, 1u, leader);
-        umma_ts(tmem_base + C_D1, ah, bl + bo, 1u, leader);
-      }
-      umma_commit(bar_d, leader);
-      __syncwarp();
-    }
+    tile_barrier();
     // ======== P3 ========
     if (worker) {
+      if (item + n_chunks < n_items) fetch(item + n_chunks);    // next tile's positions / seed: issued here, where few values are live
       if (n_done > 0) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }   // G1(t-1) reads delta1^T(t-1) and the features of tile t-1
-      stage_cols_smem(dT_hi, dT_lo, c0, t4, d2);
+      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d2);
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
       for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
         const int g = idx / mp.n_fu, f = idx % mp.n_fu;     // consecutive lanes: consecutive 16-byte granules
@@ -470,22 +530,7 @@ __global__ void __launch_bounds__(TCT, 1)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == ISSUER) {
-      const uint32_t leader = elect_one();
-      const uint64_t ah = umma_desc(sbase + mp.hT_hi, mp.rgh, 128), al = umma_desc(sbase + mp.hT_lo, mp.rgh, 128);
-      const uint64_t bh = umma_desc(sbase + mp.dT_hi, mp.rgd, 128), bl = umma_desc(sbase + mp.dT_lo, mp.rgd, 128);
-#pragma unroll
-      for (int ks = 0; ks < ROWS / 8; ++ks) {            // G2 += [h1|1]^T delta2
-        const uint64_t ao = (uint64_t)((ks * 2 * mp.rgh) >> 4), bo = (uint64_t)((ks * 2 * mp.rgd) >> 4);
-        const uint32_t acc = (n_done == 0 && ks == 0) ? 0u : 1u;
-        umma_ss(tmem_base + C_G2, ah + ao, bh + bo, IDESC, acc, leader);
-        umma_ss(tmem_base + C_G2, al + ao, bh + bo, IDESC, 1u, leader);
-        umma_ss(tmem_base + C_G2, ah + ao, bl + bo, IDESC, 1u, leader);
-      }
-      umma_commit(bar_g2, leader);
-      __syncwarp();
-    }
+    tile_barrier();
     // ======== P4 ========
     if (worker) {
       mbar_wait(bar_d, ph_d);
@@ -502,17 +547,11 @@ __global__ void __launch_bounds__(TCT, 1)
     if (worker) {
       mbar_wait(bar_g2, ph_g2);
       ph_g2 ^= 1;
-      stage_cols_smem(dT_hi, dT_lo, c0, t4, d1);
+      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == ISSUER) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t leader = elect_one();
-      issue_g1(leader, n_done == 1);
-      __syncwarp();
-    }
+    tile_barrier();
   }
 
   // ---- flush: G2 -> dW2 (+db2), G1^T -> dW1 (+db1), register partials -> dW3, db3 ------------------------------------
@@ -524,32 +563,38 @@ __global__ void __launch_bounds__(TCT, 1)
       mbar_wait(bar_g, ph_g);                            // the last commit: every MMA of this CTA has completed
       ph_g ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)c0, v2);   // lane = h1 unit (row 64: ones -> db2)
+      tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)c0, v2);   // lane = h1 unit
     } else {
 #pragma unroll
       for (int j = 0; j < UPT; ++j) v2[j] = 0.f;          // this CTA had no tile: the slab must still be defined
     }
-    if (row < H) {
+    // M = 64 accumulators: lanes 0-15, 32-47, 64-79, 96-111 hold units 0-15, 16-31, 32-47, 48-63
+    const bool lane_ok = (row & 16) == 0;
+    const int unit = (row >> 5) * 16 + (row & 15);
+    if (lane_ok) {
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) slab[o_W2 + row * H + c0 + j] = v2[j];
-    } else if (row == H) {
-#pragma unroll
-      for (int j = 0; j < UPT; ++j) slab[o_b2 + c0 + j] = v2[j];
+      for (int j = 0; j < UPT; ++j) slab[o_W2 + unit * H + c0 + j] = v2[j];
     }
-    // G1^T: lane = delta1 unit, column = feature (column F: ones -> db1); 8 columns per read, groups dealt over quarters
+    // G1^T / GB: lane = delta1 / delta2 unit, column = feature (column F: ones -> db1 / db2); 8 columns per read,
+    // column groups dealt over the quarters
     for (int cg = quarter; cg < mp.n_g1 / 8; cg += NQ) {
-      float v1[8];
-      if (any) tmem_ld8(tmem_base + lane_base + C_G1 + (uint32_t)(8 * cg), v1);
-      else {
+      float v1[8], vb[8];
+      if (any) {
+        tmem_ld8(tmem_base + lane_base + C_G1 + (uint32_t)(8 * cg), v1);
+        tmem_ld8(tmem_base + lane_base + C_GB + (uint32_t)(8 * cg), vb);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v1[j] = 0.f;
+        for (int j = 0; j < 8; ++j) v1[j] = vb[j] = 0.f;
       }
-      if (row < H) {
+      if (lane_ok) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int f = 8 * cg + j;
-          if (f < F) slab[o_W1 + f * H + row] = v1[j];
-          else if (f == F) slab[o_b1 + row] = v1[j];
+          if (f < F) slab[o_W1 + f * H + unit] = v1[j];
+          else if (f == F) {
+            slab[o_b1 + unit] = v1[j];
+            slab[o_b2 + unit] = vb[j];
+          }
         }
       }
     }
@@ -564,8 +609,8 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  for (int q = tid; q < H; q += TCT) slab[o_W3 + q] = redS[q];
+  tile_barrier();
+  for (int q = tid; q < H; q += TCW) slab[o_W3 + q] = redS[q];
   if (tid == 0) slab[o_b3] = redS[H];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
@@ -600,7 +645,7 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   const DevSys& s = ctx->sys;
   if (s.H != H) return NQMC_ERR_UNSUPPORTED;
   const SmemMap mp = make_map(s.F);
-  if (mp.total > SMEM_LIMIT || s.F + 1 > 64) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
+  if (mp.total > SMEM_LIMIT || mp.n_g1 > 32) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
   if (const char* e = getenv("NQMC_TC_BWD"))
     if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
   const int64_t nwb = (W + ROWS - 1) / ROWS;
