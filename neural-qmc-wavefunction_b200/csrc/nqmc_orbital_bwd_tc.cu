@@ -62,7 +62,7 @@ constexpr int NRG = ROWS / 4;         // 32 row groups (granule = 4 consecutive 
 constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                                                   = 16384 B
 
 struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
-  int hM_hi, hM_lo, dM_hi, dM_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, misc, total;
+  int hM_hi, hM_lo, dM_hi, dM_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, pf, misc, total;
   int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the (K-major) feature buffer
   int n_g1;           // N of the [f|1] MMAs (a multiple of 8): columns >= n_fu read into the next row group, ignored
 };
@@ -83,6 +83,7 @@ __host__ __device__ inline SmemMap make_map(int F) {
   m.fT_hi = o; o += NRG * m.rgf;
   m.fT_lo = o; o += NRG * m.rgf;
   m.fstage = o; o += m.n_fu * FS_LD * 4;
+  m.pf = o; o += 5 * ROWS * 4;        // next tile: x, y, z, weight, inverse-matrix entry per row (cp.async targets)
   m.misc = o; o += (F * H + 3 * H + H + 8) * 4 + 64;
   m.total = o;
   return m;
@@ -316,21 +317,34 @@ __global__ void __launch_bounds__(TCT, 1)
   // [f|1] products: D=f32, A=B=tf32, A MN-major (delta), B K-major (features), M = 64 delta units, N = n_g1
   const uint32_t idesc_g1 =
       (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(mp.n_g1 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-  // positions and reverse seed of one tile row; the next tile's are fetched while the current one computes
-  float nx = 0.f, ny = 0.f, nz = 0.f, nwt = 1.f, ninv = 0.f;     // raw loads; consumed one tile later
+  // Positions and reverse seed of one tile row.  The next tile's are fetched while the current one computes: the
+  // quarter-0 thread of each row issues five 4-byte cp.async into shared memory (no registers held across the tile --
+  // register prefetch was spilled by ptxas, and a spilled load stalls on the spot), waits for them at the end of P3
+  // and the tile barrier there publishes them to the row's four threads.
+  float* pf = reinterpret_cast<float*>(smem + mp.pf);            // [5][ROWS]
   auto fetch = [&](const int64_t item) {
     const int i = (int)(item % ns);
     int64_t w = (item / ns) * ROWS + row;
     if (w >= W) w = W - 1;
     const int e = elec0 + i;
-    nx = r[(int64_t)(3 * e + 0) * W + w];
-    ny = r[(int64_t)(3 * e + 1) * W + w];
-    nz = r[(int64_t)(3 * e + 2) * W + w];
-    if (wgt != nullptr) nwt = wgt[w];
-    else if (e_l != nullptr) nwt = e_l[w];
-    ninv = inv[(int64_t)ent_index(s, spin, i, korb) * W + w];
+    const float* src[5] = {r + (int64_t)(3 * e + 0) * W + w, r + (int64_t)(3 * e + 1) * W + w, r + (int64_t)(3 * e + 2) * W + w,
+                           wgt != nullptr ? wgt + w : (e_l != nullptr ? e_l + w : nullptr),
+                           inv + (int64_t)ent_index(s, spin, i, korb) * W + w};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      if (src[q] != nullptr)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(pf + q * ROWS + row)), "l"(src[q]) : "memory");
+      else
+        pf[q * ROWS + row] = 1.0f;
+    }
   };
-  if (worker && chunk < n_items) fetch(chunk);
+  if (worker && chunk < n_items) {
+    if (quarter == 0) {
+      fetch(chunk);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(TCW) : "memory");      // workers only
+  }
   // Pipeline (one tile = 3 CTA barriers; delta1 of tile t stays in registers until tile t+1's first phase, so the
   // wait for G2(t) -- which still reads the buffer delta1^T goes into -- hides behind layer 1 of tile t+1):
   //   P1  layer 1(t) -> A(h1) in TMEM ; delta1(t-1) -> dM                   | issue U2(t), G1^T(t-1) = delta1^T [f|1]
@@ -431,8 +445,9 @@ __global__ void __launch_bounds__(TCT, 1)
     float h1[UPT], d2[UPT], seed = 0.f;
     // ======== P1 ========
     if (worker) {
-      const float x = nx, y = ny, z = nz;
+      const float x = pf[0 * ROWS + row], y = pf[1 * ROWS + row], z = pf[2 * ROWS + row];
       {
+        const float nwt = pf[3 * ROWS + row], ninv = pf[4 * ROWS + row];
         float wt = nwt;
         if (wgt == nullptr && e_l != nullptr) wt = isfinite(nwt) ? nwt - centerf : 0.f;
         seed = wt * ninv;
@@ -513,7 +528,8 @@ __global__ void __launch_bounds__(TCT, 1)
     tile_barrier();
     // ======== P3 ========
     if (worker) {
-      if (item + n_chunks < n_items) fetch(item + n_chunks);    // next tile's positions / seed: issued here, where few values are live
+      const bool more = item + n_chunks < n_items;
+      if (more && quarter == 0) fetch(item + n_chunks);         // next tile's positions / seed (read last in P1, two barriers ago)
       if (n_done > 0) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }   // G1(t-1) reads delta1^T(t-1) and the features of tile t-1
       stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d2);
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
@@ -528,6 +544,7 @@ __global__ void __launch_bounds__(TCT, 1)
         *reinterpret_cast<float4*>(smem + mp.fT_hi + g * mp.rgf + f * 16) = h4;
         *reinterpret_cast<float4*>(smem + mp.fT_lo + g * mp.rgf + f * 16) = l4;
       }
+      if (more && quarter == 0) asm volatile("cp.async.wait_all;" ::: "memory");   // the barrier below publishes the prefetch
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tile_barrier();
