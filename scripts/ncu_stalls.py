@@ -14,7 +14,12 @@ for i, r in enumerate(rows):
         h = i
         break
 hdr = rows[h]
-data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[h + 1:]:          # multi-kernel reports repeat the header: summarise the first kernel only
+    if r and r[0] == "Address":
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 isrc, iex, ins = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [i for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
 tot = sum(int(r[ins] or 0) for r in data)
