@@ -25,7 +25,7 @@ constexpr int H = 64;
 constexpr int NQ = 4;
 constexpr int TCW = 128 * NQ;
 constexpr int NWW = TCW / 32;          // worker warps
-constexpr int TCT = TCW + 32;
+constexpr int TCT = TCW + 128;         // 16 worker warps + the issuer warpgroup (one issuing warp; see setmaxnreg below)
 constexpr int ROWS = 128;
 constexpr int CH = 5;
 constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(TCT, 1)
 
   if (!worker) {
     // =============================== MMA issuer warp =====================================================
+    // register split (as in nqmc_orbital_bwd_tc.cu): 20 warps x 96 at launch -> 112 per worker, 32 per issuer thread
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    if (warp != NWW) return;                                  // three warps only complete the warpgroup
     const uint32_t leader = elect_one();
     const uint64_t dBh = umma_desc(smem_u32(Bhi), B_K4, 128), dBl = umma_desc(smem_u32(Blo), B_K4, 128);
     uint32_t g = 0, t = 0;                                     // global chunk counter, local tile counter
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   } else {
     // =============================== worker warps ========================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t g = 0, t = 0;
     float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  asm volatile("bar.sync 2, %0;" ::"n"(TCW + 32) : "memory");   // workers + the issuing warp (the idle warps have left)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
