@@ -644,25 +644,35 @@ __global__ void __launch_bounds__(NT, (H <= 64) ? 2 : 1)
   if (tid == 0) slab[o_b3] = redS[2 * H];
 }
 
-// reduce per-CTA slabs of every network into the fp64 output (theta order): one warp per group of
-// 32 consecutive slab entries would be coalesced already; here each thread owns one entry and the
-// chunk loop is unrolled by 4 for memory-level parallelism.
-__global__ void orb_bwd_reduce_kernel(const DevSys s, const float* __restrict__ part, const int n_chunks, const int p_mlp,
-                                      double* __restrict__ out) {
+// reduce per-CTA slabs of every network into the fp64 output (theta order)
+__global__ void __launch_bounds__(256) orb_bwd_reduce_kernel(const DevSys s, const float* __restrict__ part, const int n_chunks,
+                                                             const int p_mlp, double* __restrict__ out) {
+  // block = 32 consecutive slab entries x 8 chunk groups: thread (g, lane) sums the slabs c = g, g+8, ... of entry
+  // 32 blockIdx.x + lane (coalesced, all loads of a thread independent), then the 8 partial sums are added in a
+  // fixed order (deterministic) through shared memory.
+  __shared__ double sm[8][33];
   const int m = blockIdx.y;
   const MlpOff off = s.mlp[m];
   const int H = s.H, F = s.F;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p_mlp; idx += gridDim.x * blockDim.x) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int c = 0;
-    for (; c + 3 < n_chunks; c += 4) {
-      a0 += (double)part[(int64_t)((c + 0) * s.n_mlp + m) * p_mlp + idx];
-      a1 += (double)part[(int64_t)((c + 1) * s.n_mlp + m) * p_mlp + idx];
-      a2 += (double)part[(int64_t)((c + 2) * s.n_mlp + m) * p_mlp + idx];
-      a3 += (double)part[(int64_t)((c + 3) * s.n_mlp + m) * p_mlp + idx];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  double a = 0.0;
+  if (idx < p_mlp) {
+    double a0 = 0.0, a1 = 0.0;
+    int c = g;
+    for (; c + 8 < n_chunks; c += 16) {
+      a0 += (double)part[(int64_t)(c * s.n_mlp + m) * p_mlp + idx];
+      a1 += (double)part[(int64_t)((c + 8) * s.n_mlp + m) * p_mlp + idx];
     }
-    for (; c < n_chunks; ++c) a0 += (double)part[(int64_t)(c * s.n_mlp + m) * p_mlp + idx];
-    const double acc = (a0 + a1) + (a2 + a3);
+    if (c < n_chunks) a0 += (double)part[(int64_t)(c * s.n_mlp + m) * p_mlp + idx];
+    a = a0 + a1;
+  }
+  sm[g][lane] = a;
+  __syncthreads();
+  if (g == 0 && idx < p_mlp) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += sm[q][lane];
     // slab order: b1[H] W1[F*H] b2[H] W2[H*H] b3 W3[H]
     int o;
     if (idx < H) o = off.b1 + idx;
@@ -739,7 +749,7 @@ int launch_bwd_t(nqmc_ctx* ctx, const float* r, const float* wgt, const double* 
                                                ctx->p_mlp);
   }
   NQMC_LAUNCH_CHECK();
-  dim3 g((ctx->p_mlp + 255) / 256, s.n_mlp);
+  dim3 g((ctx->p_mlp + 31) / 32, s.n_mlp);
   orb_bwd_reduce_kernel<<<g, 256, 0, st>>>(s, ctx->part_mlp, n_chunks, ctx->p_mlp, out);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
@@ -786,7 +796,7 @@ int nq_launch_orb_bwd(nqmc_ctx* ctx, const float* r, const float* wgt, const dou
     int nc = 0;
     int rc = nq_launch_orb_bwd_tc(ctx, r, wgt, hdr_center, e_l, W, &nc, st);
     if (rc == NQMC_OK) {
-      dim3 g((ctx->p_mlp + 255) / 256, ctx->sys.n_mlp);
+      dim3 g((ctx->p_mlp + 31) / 32, ctx->sys.n_mlp);
       orb_bwd_reduce_kernel<<<g, 256, 0, st>>>(ctx->sys, ctx->part_mlp, nc, ctx->p_mlp, out);
       NQMC_LAUNCH_CHECK();
       return NQMC_OK;
