@@ -341,8 +341,16 @@ __global__ void stats13_finish_kernel(const double* __restrict__ part, const int
   nq_pdl_trigger();                                    // the reverse pass behind this kernel may start staging its weights
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double a = 0;
-  if (slot < 13)
-    for (int b = lane; b < nblk; b += 32) a += part[(int64_t)b * NPART + slot];
+  if (slot < 13) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;             // four independent loads per round (latency, not bandwidth, matters here)
+    for (int b = lane; b < nblk; b += 128) {
+      a0 += part[(int64_t)b * NPART + slot];
+      if (b + 32 < nblk) a1 += part[(int64_t)(b + 32) * NPART + slot];
+      if (b + 64 < nblk) a2 += part[(int64_t)(b + 64) * NPART + slot];
+      if (b + 96 < nblk) a3 += part[(int64_t)(b + 96) * NPART + slot];
+    }
+    a = (a0 + a1) + (a2 + a3);
+  }
   a = warp_sum(a);
   if (lane == 0) {
     if (slot < 5) hdr[slot] = a;
