@@ -328,6 +328,12 @@ def run_ours(args):
                          "hbm_gbs_measured": pk.get("hbm_gbs"),
                          "whole_step_achieved_tflops": flops_step * Wl / (total_ms / args.steps * 1e-3) / 1e12,
                          "kernel_ms": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
+                         # algorithmic TFLOP/s of the three orbital kernels (value 2mE, Laplacian 5 x 2mE,
+                         # parameter gradient 2 x 2mE per walker) and their fraction of the 3xTF32 tensor peak
+                         "kernel_tflops": {k: (mult * flops_value * Wl / (prof[k][0] / max(prof[k][1], 1) * 1e-3) / 1e12)
+                                           for k, mult in (("eval1", 1.0), ("eval5", 5.0), ("bwd", 2.0)) if prof[k][1]},
+                         "kernel_frac_of_tf32_over_3": {k: (mult * flops_value * Wl / (prof[k][0] / max(prof[k][1], 1) * 1e-3) / 1e12) / peak3
+                                                        for k, mult in (("eval1", 1.0), ("eval5", 5.0), ("bwd", 2.0)) if prof[k][1]},
                          "kernel_launches": {k: v[1] for k, v in prof.items()}},
             "sanity": {"mean_E_L": h[1] / max(h[0], 1), "n_finite": h[0], "n_bad": h[4], "acceptance": h[3] / (world * Wl)},
         }

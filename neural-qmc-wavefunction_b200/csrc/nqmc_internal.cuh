@@ -242,6 +242,7 @@ int nq_launch_orb_eval5_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi,
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                          int* n_chunks_out, cudaStream_t st);
 int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
+int nq_launch_orb_eval1_l1tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);   // both layers on tensor cores
 int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,
                  float clip, double* norm_out, cudaStream_t st);
 int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,

@@ -761,7 +761,8 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
   const int H = ctx->sys.H;
   if (channels == 1) {
     if (ctx->use_tc) {
-      int rc = nq_launch_orb_eval1_tc(ctx, r, W, phi, st);
+      int rc = nq_launch_orb_eval1_l1tc(ctx, r, W, phi, st);                            // both layers on tensor cores (A <= 6)
+      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_eval1_tc(ctx, r, W, phi, st);  // layer 1 on the FP32 pipe
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
     if (H == 32) return launch_eval_t<32, 1, 8, 256>(ctx, r, W, phi, st);
