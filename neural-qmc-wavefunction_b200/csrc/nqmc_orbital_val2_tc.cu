@@ -5,7 +5,7 @@
 // real VMC iteration (10 value-only MH steps per sampled step with the reference defaults, vmc.py:247).
 //
 // Why: in the FP32-layer-1 kernel two thirds of a thread's instructions are the 11 x 16 FFMAs of layer 1 and their
-// weight loads.  Here a row's features [x, y, z, d_A.., exp(-d_A).., 1] (K1 = 16 columns incl. the ones column that
+// weight loads.  Here a row's features [x, y, z, 1, (d_A, exp(-d_A)) pairs] (K1 = 16 columns; the ones column
 // carries b1) are written as tf32 hi/lo into TENSOR MEMORY by the four threads of the row (one nucleus each) and
 // layer 1 becomes 6 UMMAs (M=128, N=64, K=8); a thread is left with about 330 instructions per tile instead of 830:
 //     W_a  features of tile t+2            -> FA[b]   (tcgen05.st)           | issuer: D1[b] = FA[b] x [W1;b1]
@@ -28,7 +28,7 @@ constexpr int NWW = TCW / 32;
 constexpr int NSYNC = TCW + 64;       // workers + the two issuing warps
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // 16
-constexpr int K1 = 16;                // layer-1 K: features + ones column, padded (3 + 2 A + 1 <= 16  ->  A <= 6)
+constexpr int K1 = 16;                // layer-1 K: x, y, z, 1, (d_a, exp(-d_a)) pairs, padded (4 + 2 A <= 16  ->  A <= 6)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t C_FA = 0, C_D = 64, C_A2 = 192;     // FA[b] = C_FA + 32 b (hi 16 | lo 16); D1/U2[b] = C_D + 64 b; A2[b] = C_A2 + 128 b (hi 64 | lo 64)
 constexpr int W2B = (H / 4) * H * 16;  // one W2 copy (hi or lo), K-major no swizzle [k/4][n][k%4]: 16 KB
@@ -87,19 +87,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t a) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(a) : "memory");
-}
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(a) & 0xFFFFE000u;
   lo = __float_as_uint(a - __uint_as_float(hi));
 }
-// one feature of this thread's row -> column f (hi) and K1 + f (lo) of the feature operand
-__device__ __forceinline__ void put_feature(uint32_t fa, int f, float v) {
-  uint32_t hi, lo;
-  split_tf32(v, hi, lo);
-  tmem_st1(fa + (uint32_t)f, hi);
-  tmem_st1(fa + (uint32_t)(K1 + f), lo);
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 __global__ void __launch_bounds__(TCT, 1)
@@ -125,7 +121,7 @@ __global__ void __launch_bounds__(TCT, 1)
   const int ns = spin == 0 ? s.n_up : s.n_dn;
   const int elec0 = spin == 0 ? 0 : s.n_up;
   const MlpOff off = s.mlp[m];
-  const int A = s.A, F = s.F;
+  const int A = s.A;
 
   // ---- setup: weights to tf32 hi/lo operand layouts (reads theta only) ------------------------------------------
   for (int q = tid; q < H; q += TCT) {
@@ -149,7 +145,11 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   for (int idx = tid; idx < K1 * H; idx += TCT) {
     const int k = idx / H, n = idx % H;
-    const float v = k < F ? theta[off.W1 + k * H + n] : (k == F ? theta[off.b1 + n] : 0.f);
+    // feature order of the operand: x, y, z, 1, then (d_a, exp(-d_a)) pairs -- each thread's columns are contiguous
+    float v = 0.f;
+    if (k < 3) v = theta[off.W1 + k * H + n];
+    else if (k == 3) v = theta[off.b1 + n];
+    else if (k < 4 + 2 * A) v = theta[off.W1 + (((k - 4) & 1) ? 3 + A + ((k - 4) >> 1) : 3 + ((k - 4) >> 1)) * H + n];
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int o = (k >> 2) * (H * 4) + n * 4 + (k & 3);
@@ -249,19 +249,23 @@ __global__ void __launch_bounds__(TCT, 1)
       const float x = nx, y = ny, z = nz;
       if (st + 3 < n_tiles) fetch(st + 3);
       const uint32_t fa = tmem_base + lane_base + C_FA + 32u * (uint32_t)((st + 2) & 1);
-      if (quarter == 0) {
-        put_feature(fa, 0, x);
-        put_feature(fa, 1, y);
-        put_feature(fa, 2, z);
-        tmem_st1(fa + (uint32_t)F, 0x3f800000u);                // ones column (carries b1); its lo part stays 0
+      if (quarter == 0) {                                       // columns 0..3: x, y, z, 1 (the ones column carries b1)
+        uint32_t h0, l0, h1, l1, h2, l2;
+        split_tf32(x, h0, l0);
+        split_tf32(y, h1, l1);
+        split_tf32(z, h2, l2);
+        tmem_st4(fa, h0, h1, h2, 0x3f800000u);
+        tmem_st4(fa + K1, l0, l1, l2, 0u);
       }
-      for (int a = quarter; a < A; a += NQ) {
+      for (int a = quarter; a < A; a += NQ) {                  // columns 4 + 2a, 5 + 2a: d_a, exp(-d_a)
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        put_feature(fa, 3 + a, dd);
-        put_feature(fa, 3 + A + a, __expf(-dd));
+        uint32_t h0, l0, h1, l1;
+        split_tf32(dd, h0, l0);
+        split_tf32(__expf(-dd), h1, l1);
+        tmem_st2(fa + (uint32_t)(4 + 2 * a), h0, h1);
+        tmem_st2(fa + (uint32_t)(K1 + 4 + 2 * a), l0, l1);
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     // ---- W_b: h1 = tanh(D1) of tile st+1 -> A2[(st+1)&1]
     if (st + 1 >= 0 && st + 1 < n_tiles) {
@@ -276,7 +280,6 @@ __global__ void __launch_bounds__(TCT, 1)
       for (int j = 0; j < UPT; ++j) split_tf32(nq_tanh(v[j]), hi[j], lo[j]);
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)c0, hi);
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)(H + c0), lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     // ---- W_c: phi of tile st
     float out = 0.f;
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(TCT, 1)
       for (int j = 0; j < UPT; ++j) out = fmaf(W3s[c0 + j], nq_tanh(v[j] + b2s[c0 + j]), out);
       if (quarter != 0) outS[(pb * (NQ - 1) + quarter - 1) * ROWS + row] = out;
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // feature and h1 stores of this step
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tile_barrier();        // FA(st+2), A2(st+1) complete; D1/U2 of tile st read; partial outputs visible
     if (st >= 0 && quarter == 0) {
