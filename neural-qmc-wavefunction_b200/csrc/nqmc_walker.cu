@@ -81,11 +81,14 @@ __device__ __forceinline__ void pade(float r, float a, float b, float& u, float&
 
 // Jastrow + cusps on physical coordinates.  Accumulates value J, gradient g[e][3], Laplacian lap,
 // and the bare potentials.  LAP=false: value only.
+// jpar != nullptr: also d J / d(a_ee, a_en, b_ee, b_en) of the Pade terms (u = a d q, q = 1 / (1 + b d):
+// du/da = d q, du/db = -a d^2 q^2), taken in the same pair loop.
 template <int NE, bool LAP>
 __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float* __restrict__ theta, const float (&x)[NE],
                                                    const float (&y)[NE], const float (&z)[NE], float& J,
                                                    float (&gx)[NE], float (&gy)[NE], float (&gz)[NE], float& lap,
-                                                   float& ven, float& vee) {
+                                                   float& ven, float& vee, float* jpar = nullptr) {
+  float g_aee = 0.f, g_aen = 0.f, g_bee = 0.f, g_ben = 0.f;
   const float a_ee = theta[s.jas_a_ee], b_ee = theta[s.jas_b_ee];
   const float a_en = theta[s.jas_a_en], b_en = theta[s.jas_b_en];
   const float cb = s.use_cusp ? fabsf(theta[s.ee_cusp_b]) : 0.f;
@@ -100,6 +103,11 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
           float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
           float u, up, upp;
           pade(d, a_ee, b_ee, u, up, upp);
+          if (jpar != nullptr) {
+            const float q = 1.0f / fmaf(b_ee, d, 1.0f);
+            g_aee = fmaf(d, q, g_aee);
+            g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
+          }
           if (s.use_cusp) {
             const bool same = (i < s.n_up) == (j < s.n_up);
             float u2, up2, upp2;
@@ -121,6 +129,11 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
         float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
         float u, up, upp;
         pade(d, a_en, b_en, u, up, upp);
+        if (jpar != nullptr) {
+          const float q = 1.0f / fmaf(b_en, d, 1.0f);
+          g_aen = fmaf(d, q, g_aen);
+          g_ben = fmaf(-a_en * d * d, q * q, g_ben);
+        }
         if (s.use_cusp) {
           // -Z d + d g_A(d),  g_A = W1 . tanh(W0^T [d, d^2, e^-d] + b0) + b1  (phase3-issue-body.md:66-81)
           const float e = __expf(-d);
@@ -161,6 +174,9 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
         }
       }
     }
+  if (jpar != nullptr) {
+    jpar[0] = g_aee; jpar[1] = g_aen; jpar[2] = g_bee; jpar[3] = g_ben;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,7 +185,8 @@ template <int NS, bool ENERGY>
 __device__ __forceinline__ void walker_eval(const DevSys& s, const float* __restrict__ theta,
                                             const float* __restrict__ r, const float* __restrict__ phi,
                                             float* __restrict__ inv_out, const int64_t W, const int64_t w,
-                                            float& logabs, float& sign, float& T, float& ven, float& vee) {
+                                            float& logabs, float& sign, float& T, float& ven, float& vee,
+                                            float* jpar = nullptr) {
   constexpr int NE = 2 * NS;
   float x[NE], y[NE], z[NE], gx[NE], gy[NE], gz[NE];
 #pragma unroll
@@ -233,7 +250,7 @@ __device__ __forceinline__ void walker_eval(const DevSys& s, const float* __rest
     }
   }
   float J, lapJ;
-  jastrow_cusp_terms<NE, ENERGY>(s, theta, x, y, z, J, gx, gy, gz, lapJ, ven, vee);
+  jastrow_cusp_terms<NE, ENERGY>(s, theta, x, y, z, J, gx, gy, gz, lapJ, ven, vee, jpar);
   logabs += J;
   T = 0.f;
   if (ENERGY) {
@@ -289,33 +306,14 @@ __global__ void __launch_bounds__(WT) assemble_stats_kernel(const DevSys s, cons
 #pragma unroll
   for (int i = 0; i < 13; ++i) acc[i] = 0.0;
   if (valid) {
-    float la, sg, T, ven, vee;
-    walker_eval<NS, true>(s, theta, r, phi, inv_out, W, w, la, sg, T, ven, vee);
+    float la, sg, T, ven, vee, jp[4];
+    walker_eval<NS, true>(s, theta, r, phi, inv_out, W, w, la, sg, T, ven, vee, jp);   // jp: Jastrow log-derivatives from the same pair loop
     const float e = T + ven + vee + s.v_nn;            // molecular.py:175
     e_l[w] = e;
     if (acc_flag) acc[3] = acc_flag[w];
     if (isfinite(e)) {
       acc[0] = 1.0; acc[1] = e; acc[2] = (double)e * e;
-      const float a_ee = theta[s.jas_a_ee], b_ee = theta[s.jas_b_ee];
-      const float a_en = theta[s.jas_a_en], b_en = theta[s.jas_b_en];
-      float g_aee = 0.f, g_bee = 0.f, g_aen = 0.f, g_ben = 0.f;
-      for (int i = 0; i < s.N; ++i) {
-        const float xi = r[(int64_t)(3 * i) * W + w], yi = r[(int64_t)(3 * i + 1) * W + w], zi = r[(int64_t)(3 * i + 2) * W + w];
-        for (int j = i + 1; j < s.N; ++j) {
-          const float dx = xi - r[(int64_t)(3 * j) * W + w], dy = yi - r[(int64_t)(3 * j + 1) * W + w], dz = zi - r[(int64_t)(3 * j + 2) * W + w];
-          const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-          const float q = 1.0f / fmaf(b_ee, d, 1.0f);
-          g_aee = fmaf(d, q, g_aee);
-          g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
-        }
-        for (int a = 0; a < s.A; ++a) {
-          const float dx = xi - s.R[3 * a], dy = yi - s.R[3 * a + 1], dz = zi - s.R[3 * a + 2];
-          const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-          const float q = 1.0f / fmaf(b_en, d, 1.0f);
-          g_aen = fmaf(d, q, g_aen);
-          g_ben = fmaf(-a_en * d * d, q * q, g_ben);
-        }
-      }
+      const float g_aee = jp[0], g_aen = jp[1], g_bee = jp[2], g_ben = jp[3];
       acc[5] = g_aee; acc[6] = g_aen; acc[7] = g_bee; acc[8] = g_ben;
       acc[9] = (double)e * g_aee; acc[10] = (double)e * g_aen; acc[11] = (double)e * g_bee; acc[12] = (double)e * g_ben;
     } else {
