@@ -73,7 +73,7 @@ __device__ __forceinline__ void inv_slogdet(const int n, float (&a)[NS][NS], flo
 
 // Pade pair term u = a r / (1 + b r) and derivatives
 __device__ __forceinline__ void pade(float r, float a, float b, float& u, float& up, float& upp) {
-  float q = 1.0f / fmaf(b, r, 1.0f);
+  float q = __fdividef(1.0f, fmaf(b, r, 1.0f));      // 2-ulp reciprocal: the IEEE division sequence is ~8 instructions per pair
   u = a * r * q;
   up = a * q * q;
   upp = -2.0f * a * b * q * q * q;
@@ -100,11 +100,14 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
       for (int j = i + 1; j < NE; ++j)
         if (j < s.N) {
           float dx = x[i] - x[j], dy = y[i] - y[j], dz = z[i] - z[j];
-          float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          // d and 1/d from one rsqrt (2 ulp) instead of an IEEE sqrt and an IEEE division
+          const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+          const float id = rsqrtf(r2);
+          float d = r2 > 0.f ? r2 * id : 0.f;
           float u, up, upp;
           pade(d, a_ee, b_ee, u, up, upp);
           if (jpar != nullptr) {
-            const float q = 1.0f / fmaf(b_ee, d, 1.0f);
+            const float q = __fdividef(1.0f, fmaf(b_ee, d, 1.0f));
             g_aee = fmaf(d, q, g_aee);
             g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
           }
@@ -116,7 +119,6 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
           }
           J += u;
           if (LAP) {
-            float id = 1.0f / d;
             float c = up * id;
             gx[i] = fmaf(c, dx, gx[i]); gy[i] = fmaf(c, dy, gy[i]); gz[i] = fmaf(c, dz, gz[i]);
             gx[j] = fmaf(-c, dx, gx[j]); gy[j] = fmaf(-c, dy, gy[j]); gz[j] = fmaf(-c, dz, gz[j]);
@@ -126,11 +128,13 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
         }
       for (int a = 0; a < s.A; ++a) {
         float dx = x[i] - s.R[3 * a], dy = y[i] - s.R[3 * a + 1], dz = z[i] - s.R[3 * a + 2];
-        float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float id = rsqrtf(r2);
+        float d = r2 > 0.f ? r2 * id : 0.f;
         float u, up, upp;
         pade(d, a_en, b_en, u, up, upp);
         if (jpar != nullptr) {
-          const float q = 1.0f / fmaf(b_en, d, 1.0f);
+          const float q = __fdividef(1.0f, fmaf(b_en, d, 1.0f));
           g_aen = fmaf(d, q, g_aen);
           g_ben = fmaf(-a_en * d * d, q * q, g_ben);
         }
@@ -166,11 +170,10 @@ __device__ __forceinline__ void jastrow_cusp_terms(const DevSys& s, const float*
         }
         J += u;
         if (LAP) {
-          float id = 1.0f / d;
           float c = up * id;
           gx[i] = fmaf(c, dx, gx[i]); gy[i] = fmaf(c, dy, gy[i]); gz[i] = fmaf(c, dz, gz[i]);
           lap += upp + 2.0f * c;
-          ven -= s.Z[a] / fmaxf(d, 1e-10f);            // molecular.py:97-100
+          ven -= s.Z[a] * fminf(id, 1e10f);            // Z / max(d, 1e-10)   (molecular.py:97-100)
         }
       }
     }
