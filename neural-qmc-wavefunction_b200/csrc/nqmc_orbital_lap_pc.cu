@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TCT, 1)
         const float inv = 1.0f / dd;
         fdd[a] = dd; fex[a] = __expf(-dd); fux[a] = dx * inv; fuy[a] = dy * inv; fuz[a] = dz * inv; fti[a] = 2.0f * inv;
       }
-#pragma unroll 1
+#pragma unroll 2
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
         const int j0 = KC * kc + UPT * quarter;
         float acc[CH][UPT];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(TCT, 1)
       mbar_wait(dfull, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float out[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll
       for (int sub = 0; sub < EPC / 8; ++sub) {
         const int c0 = EPC * quarter + 8 * sub;
         float v[CH][8];
