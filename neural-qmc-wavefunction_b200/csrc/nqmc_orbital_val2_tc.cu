@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(TCT, 1)
     nz = r[(int64_t)(3 * e + 2) * W + w];
   };
   if (n_tiles > 0) fetch(0);
+#pragma unroll 2
   for (int64_t st = -2; st < n_tiles; ++st) {
     // ---- W_a: features of tile st+2 -> FA[(st+2)&1].  Quarter q takes nuclei q, q+4, ..; quarter 0 also x, y, z, 1.
     if (st + 2 < n_tiles) {
