@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(TCT, 1)
     uint32_t g = 0, t = 0;                                     // global chunk counter, local tile counter
     for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
       if (t > 0) mbar_wait(dempty, (t - 1) & 1);               // accumulators of the previous tile have been read
-#pragma unroll 1
+#pragma unroll 8
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
         const uint32_t b = g & 1, u = g >> 1;
         mbar_wait(full0 + 8 * b, u & 1);
