@@ -313,8 +313,8 @@ def run_ours(args):
                           "peak_source": "cuBLAS TF32 GEMM 8192^3 measured live in this run, divided by 3 (3xTF32 split); "
                                          "MEASURED_PEAKS.json has only a bf16 figure",
                           "tf32_dense_tflops_measured": tf32_peak,
-                          "traffic": 3.2553e6, "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum "
-                          "from the ncu --set full capture in profiles/r1e_ncu_full_metrics_eval5.txt (3.26 MB read = the walker positions, "
+                          "traffic": 3.2648e6, "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum "
+                          "from the ncu --set full capture in profiles/r1g_ncu_full_metrics_eval5.txt (3.26 MB read = the walker positions, "
                           "0 written: the 10.5 MB of orbital channels stay in the 126 MB L2 for the next kernel)",
                           "frac_of_mixed_floor": (t_floor / (ms5 / max(n5, 1) * 1e-3)) if n5 else None,
                           "mixed_floor_note": "floor = HxH-layer flops / (tf32/3) + other-layer flops / measured FFMA peak",
