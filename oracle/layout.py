@@ -58,7 +58,8 @@ class OracleSystem:
 @dataclass
 class OracleNet:
     kind: int = KIND_ANTISYMMETRIC
-    hidden: Tuple[int, int] = (64, 64)
+    hidden: Tuple[int, ...] = (64, 64)   # kind 0: any number of layers (simple.py:63-65); kind 1: two equal widths
+    activation: str = "tanh"             # kind 0 only: 'tanh' or 'silu' (simple.py:56-58)
     use_cusp: bool = False
     use_backflow: bool = False
     envelope_decay: float = 1.0      # kind 0 only (simple.py:102)
@@ -88,10 +89,8 @@ def _dense(n_in: int, n_out: int) -> Dict[str, Tuple[int, ...]]:
 def param_shapes(sysm: OracleSystem, net: OracleNet) -> Dict:
     """Nested dict of leaf shapes, mirroring the flax trees described above."""
     if net.kind == KIND_SIMPLE:
-        h0, h1 = net.hidden
-        d = 3 * sysm.n_elec
-        return {"params": {"Dense_0": _dense(d, h0), "Dense_1": _dense(h0, h1),
-                           "Dense_2": _dense(h1, 1)}}
+        dims = [3 * sysm.n_elec, *net.hidden, 1]                     # simple.py:63-68
+        return {"params": {f"Dense_{i}": _dense(dims[i], dims[i + 1]) for i in range(len(dims) - 1)}}
     h0, h1 = net.hidden
     F = 3 + 2 * sysm.n_atoms
     mlp = lambda: {"Dense_0": _dense(F, h0), "Dense_1": _dense(h0, h1), "Dense_2": _dense(h1, 1)}

@@ -89,7 +89,12 @@ class AutodiffOracle:
         s, net = self.sys, self.net
         N = s.n_elec
         if net.kind == KIND_SIMPLE:
-            mlp = self._mlp(p, "params", r.reshape(-1))                       # simple.py:51-68
+            x = r.reshape(-1)                                                 # simple.py:51-68
+            act = torch.tanh if net.activation == "tanh" else torch.nn.functional.silu
+            for i in range(len(net.hidden)):
+                x = act(x @ p[f"params/Dense_{i}/kernel"] + p[f"params/Dense_{i}/bias"])
+            nh = len(net.hidden)
+            mlp = (x @ p[f"params/Dense_{nh}/kernel"] + p[f"params/Dense_{nh}/bias"]).squeeze(-1)
             d = _safe_norm(r[:, None, :] - self.R[None, :, :])
             env = torch.sum(torch.log(torch.sum(torch.exp(-net.envelope_decay * d), dim=1)))  # simple.py:141-149
             return torch.ones((), dtype=r.dtype), mlp + env

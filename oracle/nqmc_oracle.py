@@ -88,6 +88,59 @@ def _mlp3_backward(p, prefix, cache, seed, grads: Dict[str, np.ndarray]):
     grads[prefix + "/Dense_0/kernel"] = np.einsum("wrf,wrj->wfj", f, d1)
 
 
+def _act(name, u):
+    """(sigma, sigma', sigma'') for simple.py:56-58's two activations."""
+    if name == "tanh":
+        h = np.tanh(u)
+        tp = 1.0 - h * h
+        return h, tp, -2.0 * h * tp
+    if name == "silu":
+        s = 1.0 / (1.0 + np.exp(-u))
+        return u * s, s * (1.0 + u * (1.0 - s)), s * (1.0 - s) * (2.0 + u * (1.0 - 2.0 * s))
+    raise ValueError(f"Unknown activation: {name}")
+
+
+def _mlpN(p, prefix, n_hidden, act, x, lap: bool):
+    """SimpleMLP (simple.py:51-68) with any number of hidden layers: value, Jacobian (W,D,.), Laplacian.
+    cache = per-layer (input, sigma'(u)) for the reverse pass."""
+    Wn, D = x.shape
+    h = x
+    J = np.broadcast_to(np.eye(D, dtype=x.dtype), (Wn, D, D)) if lap else None
+    L = np.zeros((Wn, D), dtype=x.dtype) if lap else None
+    cache = []
+    for i in range(n_hidden):
+        Wi, bi = p[f"{prefix}/Dense_{i}/kernel"], p[f"{prefix}/Dense_{i}/bias"]
+        u = h @ Wi + bi
+        a, a1, a2 = _act(act, u)
+        cache.append((h, a1))
+        if lap:
+            Ju = J @ Wi
+            L = a1 * (L @ Wi) + a2 * np.sum(Ju * Ju, axis=-2)
+            J = a1[:, None, :] * Ju
+        h = a
+    Wo, bo = p[f"{prefix}/Dense_{n_hidden}/kernel"], p[f"{prefix}/Dense_{n_hidden}/bias"]
+    cache.append((h, None))
+    val = (h @ Wo)[:, 0] + bo[0]
+    if lap:
+        return val, (J @ Wo)[..., 0], (L @ Wo)[:, 0], cache
+    return val, None, None, cache
+
+
+def _mlpN_backward(p, prefix, n_hidden, cache, grads):
+    """Per-walker d val / d theta for _mlpN."""
+    h_last, _ = cache[n_hidden]
+    Wn = h_last.shape[0]
+    grads[f"{prefix}/Dense_{n_hidden}/bias"] = np.ones((Wn, 1), dtype=h_last.dtype)
+    grads[f"{prefix}/Dense_{n_hidden}/kernel"] = h_last[..., None]
+    back = np.broadcast_to(p[f"{prefix}/Dense_{n_hidden}/kernel"][:, 0], h_last.shape)
+    for i in range(n_hidden - 1, -1, -1):
+        h_in, a1 = cache[i]
+        d = back * a1
+        grads[f"{prefix}/Dense_{i}/bias"] = d
+        grads[f"{prefix}/Dense_{i}/kernel"] = h_in[:, :, None] * d[:, None, :]
+        back = d @ p[f"{prefix}/Dense_{i}/kernel"].T
+
+
 def orbital_features(x, R):
     """phase2-issue-body.md:83-93: f = [x(3), |x-R_A| (A), exp(-|x-R_A|) (A)].
     x (W,n,3); returns f (W,n,F), Jf (W,n,3,F), Lf (W,n,F) (Appendix C.1 input rules)."""
@@ -304,12 +357,7 @@ class Oracle:
         Wn, N, _ = r.shape
         D = 3 * N
         x = r.reshape(Wn, D)
-        if lap:
-            Jx = np.broadcast_to(np.eye(D, dtype=r.dtype), (Wn, D, D)).copy()
-            Lx = np.zeros((Wn, D), dtype=r.dtype)
-            mlp, Jm, Lm, cache = _mlp3(p, "params", x, Jx, Lx)
-        else:
-            mlp, Jm, Lm, cache = _mlp3(p, "params", x)
+        mlp, Jm, Lm, cache = _mlpN(p, "params", len(self.net.hidden), self.net.activation, x, lap)
         alpha = self.net.envelope_decay
         diff = r[:, :, None, :] - self.sys.R[None, None].astype(r.dtype)
         d = np.sqrt(np.sum(diff * diff, -1))
@@ -361,9 +409,7 @@ class Oracle:
         Wn, N, _ = r.shape
         grads: Dict[str, np.ndarray] = {}
         if self.net.kind == KIND_SIMPLE:
-            f, h1, h2 = aux[2]
-            cache = (f[:, None, :], h1[:, None, :], h2[:, None, :])
-            _mlp3_backward(p, "params", cache, np.ones((Wn, 1), dtype=r.dtype), grads)
+            _mlpN_backward(p, "params", len(self.net.hidden), aux[2], grads)
         else:
             mats, invs = aux[2], aux[3]
             for (name, sl, ns), m, inv in zip(self._spin_slices(), mats, invs):
