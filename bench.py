@@ -102,6 +102,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.sm), "source": "nvml polled every ~1 ms during the timed steps"}
 
 
+def as_torch(x):
+    """DeviceArray -> torch CUDA tensor over the same memory (bench plumbing only)."""
+    import torch
+    if isinstance(x, torch.Tensor):
+        return x
+    t = torch.as_tensor(x, device=torch.device("cuda", x.device))
+    t._keep = x
+    return t
+
+
 def make_problem():
     from nqmc_b200.systems import hydrogen_chain
     from nqmc_b200.wavefunction import AntisymmetricWavefunction
@@ -146,7 +156,7 @@ def run_ours(args):
     peer = world > 1 and os.environ.get("NQMC_COMM", "peer") != "nccl" and parallel.attach_peer_memory(ctx)
     r = ctx.to_soa(initial_walkers(mol, Wl, lo))
     _, la = ctx.log_psi(r)
-    logp = (2.0 * la).contiguous()
+    logp = (2.0 * as_torch(la)).contiguous()
     e_l = torch.empty(Wl, dtype=torch.float32, device=dev)
     hdr = torch.empty(8, dtype=torch.float64, device=dev)
     gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
@@ -232,7 +242,7 @@ def run_ours(args):
     # ---- e2e: host buffers in pinned memory, copies inside the timed region -----------------------
     nn = 3 * mol.n_electrons
     r_host = torch.empty((Wl, mol.n_electrons, 3), dtype=torch.float32).pin_memory()
-    r_host.copy_(ctx.to_aos(r).cpu())
+    r_host.copy_(torch.from_numpy(ctx.to_aos(r).numpy()))
     logp_host = torch.empty(Wl, dtype=torch.float32).pin_memory(); logp_host.copy_(logp.cpu())
     e_host = torch.empty(Wl, dtype=torch.float32).pin_memory()
     hdr_host = torch.empty(8, dtype=torch.float64).pin_memory()
@@ -252,7 +262,7 @@ def run_ours(args):
             dist.all_reduce(hdr)
             ctx.walker_step_b(rs, e_l, hdr, gsum)
             dist.all_reduce(gsum)
-            r_host.copy_(ctx.to_aos(rs), non_blocking=True)
+            r_host.copy_(as_torch(ctx.to_aos(rs)), non_blocking=True)
             logp_host.copy_(lp, non_blocking=True)
             e_host.copy_(e_l, non_blocking=True)
             hdr_host.copy_(hdr, non_blocking=True)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NQMC_ABI_VERSION 1
+#define NQMC_ABI_VERSION 2
 
 typedef struct nqmc_ctx nqmc_ctx;
 typedef void* nqmc_stream; /* cudaStream_t */
@@ -62,14 +62,21 @@ typedef struct {
 typedef struct {
   int32_t kind;          /* NQMC_KIND_* */
   int32_t hidden0;       /* hidden_dims[0]; kind 1: 32, 64 or 128 */
-  int32_t hidden1;       /* hidden_dims[1]; kind 1: must equal hidden0 */
+  int32_t hidden1;       /* hidden_dims[1]; kind 1: must equal hidden0; kind 0: see n_hidden */
   int32_t use_cusp;      /* kind 1: ElectronNuclearCusp + ElectronElectronCusp (phase3-issue-body.md:50-122) */
   int32_t use_backflow;  /* kind 1: BackflowTransform (phase3-issue-body.md:134-169) */
   int32_t _pad;
   double envelope_decay; /* kind 0: SimpleWavefunction.envelope_decay (simple.py:102) */
   double cusp_same;      /* e-e cusp coefficient, same spin  (spec: 0.5, phase3-issue-body.md:109) */
   double cusp_diff;      /* e-e cusp coefficient, opposite   (spec: 0.25, :110) */
+  /* kind 0 only (ABI v2): SimpleMLP accepts any tuple of hidden widths and two activations
+   * (src/nqmc/wavefunction/simple.py:41,56-58,63-65).  n_hidden == 0 means "use hidden0, hidden1". */
+  int32_t n_hidden;      /* 0, or 1..6 entries of hidden[] in use */
+  int32_t activation;    /* NQMC_ACT_TANH / NQMC_ACT_SILU */
+  int32_t hidden[6];     /* hidden_dims, each 1..128 */
 } nqmc_net;
+
+enum { NQMC_ACT_TANH = 0, NQMC_ACT_SILU = 1 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 
@@ -129,6 +136,23 @@ int nqmc_log_psi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, float*
 int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed,
                  uint64_t step, int64_t walker_id0, float sigma, int64_t W, uint8_t* accept, float* n_accepted,
                  nqmc_stream stream);
+
+/* MetropolisSampler.sample on the device: n_burn moves, counters reset, n_samples * n_thin moves of which every
+ * n_thin-th position (starting with the first) is stored.  Walkers never leave the GPU and discarded positions
+ * are never materialised.
+ * Replaces: src/nqmc/sampler/metropolis.py:174-218 (two lax.scan loops, all_positions[::n_thin]).
+ * normals / uniforms: NULL (device Philox keyed by seed_burn / seed_sample, step = move index within its phase),
+ *   or explicit streams SoA [n_burn + n_samples*n_thin][3N][W] / [n_burn + n_samples*n_thin][W] (parity mode).
+ * samples   : SoA [3N][n_samples][W] (flat walker index s * W + w == the reference's reshape(-1, N, 3), vmc.py:105)
+ * n_accepted: [W] or NULL; on return the per-walker accept counts of the sampling phase (:194-199,216)
+ * sigma_dev : NULL, or a device float holding the proposal width (overrides `sigma`).  With adapt_every > 0 it is
+ *   adapted during burn-in only, every adapt_every moves: sigma *= exp((acc - target_acceptance) / sqrt(k)) for
+ *   the k-th block -- the behaviour the reference's dataclass advertises (target_acceptance, adapt_step,
+ *   metropolis.py:52-54) but never implements.  Sampling-phase moves use the final width, so detailed balance holds. */
+int nqmc_sample(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed_burn,
+                uint64_t seed_sample, int64_t walker_id0, float sigma, int64_t W, int64_t n_burn, int64_t n_samples,
+                int64_t n_thin, float* samples, float* n_accepted, float* sigma_dev, float target_acceptance,
+                int64_t adapt_every, nqmc_stream stream);
 
 /* Local energy E_L = T + V_en + V_ee + V_nn with the analytic forward-mode Laplacian.
  * Replaces: local_energy_batched / kinetic_energy / electron_nuclear_potential /
@@ -210,8 +234,33 @@ int nqmc_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t walker_id
 #define NQMC_COMM_HANDLE_BYTES 64
 int nqmc_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out);
 int nqmc_comm_attach(nqmc_ctx* ctx, const void* handles);
+int nqmc_comm_active(const nqmc_ctx* ctx); /* 1 once nqmc_comm_attach succeeded */
 /* In-place sum over ranks of vec[0..len), len <= max(param_count, NQMC_HDR_SIZE). */
 int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream stream);
+
+
+/* ---- device memory, pinned host memory, streams ------------------------------------------------------------
+ * The reference lets JAX own every array.  A host that has no array library of its own (the north_star's
+ * "no PyTorch") allocates through these; they are validated wrappers over the CUDA runtime and carry no state.
+ * Hot-path entry points keep taking caller-owned raw pointers, so XLA buffers (FFI shim) or any other device
+ * allocation work unchanged.  Errors: nqmc_mem_last_error() (thread-local). */
+enum { NQMC_COPY_H2D = 1, NQMC_COPY_D2H = 2, NQMC_COPY_D2D = 3 };
+int nqmc_device_count(void);
+int nqmc_dev_alloc(int device, size_t bytes, void** out);
+int nqmc_dev_free(int device, void* p);
+int nqmc_host_alloc(size_t bytes, void** out); /* pinned, portable */
+int nqmc_host_free(void* p);
+/* Asynchronous on `stream` (pageable host memory makes the runtime stage the copy). */
+int nqmc_dev_memcpy(int device, void* dst, const void* src, size_t bytes, int kind, nqmc_stream stream);
+/* rows x width_bytes device-to-device with pitches: stores one kept sample SoA [3N][W] into the sample tensor
+ * [3N][n_samples][W] (replaces all_positions[::n_thin], src/nqmc/sampler/metropolis.py:206-213). */
+int nqmc_dev_copy_rows(int device, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                       size_t rows, nqmc_stream stream);
+int nqmc_dev_memset(int device, void* dst, int value, size_t bytes, nqmc_stream stream);
+int nqmc_stream_create(int device, nqmc_stream* out);
+int nqmc_stream_destroy(int device, nqmc_stream stream);
+int nqmc_stream_sync(int device, nqmc_stream stream);
+const char* nqmc_mem_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,11 @@ void build_param_map(nqmc_ctx* ctx) {
   DevSys& s = ctx->sys;
   LeafBuilder lb{ctx->leaves};
   if (s.kind == NQMC_KIND_SIMPLE) {
-    s.simple = lb.mlp3("params", 3 * s.N, s.H);
+    // Dense_0 ... Dense_n in sorted-key order ("Dense_10" would sort before "Dense_2"; n <= 6 here)
+    for (int l = 0; l <= s.simple.n_hidden; ++l) {
+      const int out = l == s.simple.n_hidden ? 1 : s.simple.dim[l + 1];
+      lb.dense("params/Dense_" + std::to_string(l), s.simple.dim[l], out, s.simple.offb[l], s.simple.offW[l]);
+    }
     s.P = (int)lb.off;
     return;
   }
@@ -124,8 +128,8 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
     g_create_err = "unknown wavefunction kind";
     return NQMC_ERR_ARG;
   }
-  if (net->hidden0 != net->hidden1) {
-    g_create_err = "hidden_dims must be two equal widths";
+  if (net->kind == NQMC_KIND_ANTISYMMETRIC && net->hidden0 != net->hidden1) {
+    g_create_err = "orbital hidden_dims must be two equal widths";
     return NQMC_ERR_UNSUPPORTED;
   }
   if (net->kind == NQMC_KIND_ANTISYMMETRIC) {
@@ -137,9 +141,23 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
       g_create_err = "3 + 2*n_atoms orbital features must not exceed the hidden width";
       return NQMC_ERR_UNSUPPORTED;
     }
-  } else if (net->hidden0 < 1 || net->hidden0 > 128) {
-    g_create_err = "SimpleWavefunction hidden width must be in 1..128";
-    return NQMC_ERR_UNSUPPORTED;
+  } else {
+    if (net->n_hidden < 0 || net->n_hidden > NQMC_SIMPLE_MAX_HIDDEN) {
+      g_create_err = "SimpleWavefunction: at most 6 hidden layers";
+      return NQMC_ERR_UNSUPPORTED;
+    }
+    if (net->activation != NQMC_ACT_TANH && net->activation != NQMC_ACT_SILU) {
+      g_create_err = "Unknown activation";
+      return NQMC_ERR_ARG;
+    }
+    const int nh = net->n_hidden ? net->n_hidden : 2;
+    for (int l = 0; l < nh; ++l) {
+      const int h = net->n_hidden ? net->hidden[l] : (l == 0 ? net->hidden0 : net->hidden1);
+      if (h < 1 || h > 128) {
+        g_create_err = "SimpleWavefunction hidden widths must be in 1..128";
+        return NQMC_ERR_UNSUPPORTED;
+      }
+    }
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -190,6 +208,13 @@ int nqmc_create(const nqmc_system* sys, const nqmc_net* net, int device, nqmc_ct
     for (int d = 0; d < 3; ++d) s.R[3 * a + d] = (float)sys->R[3 * a + d];
     s.Z[a] = (float)sys->Z[a];
   }
+  if (net->kind == NQMC_KIND_SIMPLE) {
+    s.simple.n_hidden = net->n_hidden ? net->n_hidden : 2;
+    s.simple.act = net->activation;
+    s.simple.dim[0] = 3 * s.N;
+    for (int l = 0; l < s.simple.n_hidden; ++l)
+      s.simple.dim[l + 1] = net->n_hidden ? net->hidden[l] : (l == 0 ? net->hidden0 : net->hidden1);
+  }
   if (const char* e = getenv("NQMC_TC")) ctx->use_tc = atoi(e) != 0;
   ctx->want_bf = net->kind == NQMC_KIND_ANTISYMMETRIC && net->use_backflow != 0;
   build_param_map(ctx);
@@ -214,6 +239,10 @@ int nqmc_destroy(nqmc_ctx* ctx) {
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
+  for (int k = 0; k < nqmc_ctx::PROF_KINDS; ++k)
+    for (int i = 0; i < nqmc_ctx::PROF_RING; ++i)
+      for (int e = 0; e < 2; ++e)
+        if (ctx->prof_ev[k][i][e]) cudaEventDestroy(ctx->prof_ev[k][i][e]);
   delete ctx;
   return NQMC_OK;
 }
@@ -394,6 +423,43 @@ int nqmc_mh_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals, con
   return mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, accept, n_acc, S(st));
 }
 
+int nqmc_sample(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms, uint64_t seed_burn,
+                uint64_t seed_sample, int64_t wid0, float sigma, int64_t W, int64_t n_burn, int64_t n_samples,
+                int64_t n_thin, float* samples, float* n_acc, float* sigma_dev, float target_acceptance,
+                int64_t adapt_every, nqmc_stream st_) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !logp || n_burn < 0 || n_samples < 0 || n_thin < 1 || (n_samples > 0 && !samples)) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = S(st_);
+  const size_t nn = 3 * (size_t)ctx->sys.N, w = (size_t)W;
+  float* cnt = n_acc ? n_acc : ctx->nacc_stage;
+  const bool adapt = sigma_dev != nullptr && adapt_every > 0;
+  ctx->sigma_dev = sigma_dev;
+  struct Reset { nqmc_ctx* c; ~Reset() { c->sigma_dev = nullptr; } } reset{ctx};
+  if ((rc = nq_fill(ctx, cnt, 0.f, W, st))) return rc;                        // metropolis.py:177-182
+  int64_t t_all = 0;
+  for (int64_t t = 0; t < n_burn; ++t, ++t_all) {                             // metropolis.py:185-191
+    rc = mh_core(ctx, r, logp, normals ? normals + t_all * nn * w : nullptr, uniforms ? uniforms + t_all * w : nullptr,
+                 seed_burn, (uint64_t)t, wid0, sigma, W, nullptr, cnt, st);
+    if (rc) return rc;
+    if (adapt && (t + 1) % adapt_every == 0) {
+      const float gain = 1.0f / sqrtf((float)((t + 1) / adapt_every));
+      if ((rc = nq_adapt_sigma(ctx, cnt, W, (int)adapt_every, target_acceptance, gain, sigma_dev, st))) return rc;
+    }
+  }
+  if ((rc = nq_fill(ctx, cnt, 0.f, W, st))) return rc;                        // metropolis.py:194-199
+  for (int64_t t = 0; t < n_samples * n_thin; ++t, ++t_all) {                 // metropolis.py:202-210
+    rc = mh_core(ctx, r, logp, normals ? normals + t_all * nn * w : nullptr, uniforms ? uniforms + t_all * w : nullptr,
+                 seed_sample, (uint64_t)t, wid0, sigma, W, nullptr, cnt, st);
+    if (rc) return rc;
+    if (t % n_thin == 0)                                                      // all_positions[::n_thin] (:213)
+      NQMC_CUDA(cudaMemcpy2DAsync(samples + (size_t)(t / n_thin) * w, (size_t)n_samples * w * sizeof(float), r,
+                                  w * sizeof(float), w * sizeof(float), nn, cudaMemcpyDeviceToDevice, st));
+  }
+  return NQMC_OK;
+}
+
 static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
   ctx->jas_valid_for = nullptr;
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
@@ -517,6 +583,8 @@ int nqmc_comm_attach(nqmc_ctx* ctx, const void* handles) {
   NQMC_CUDA(cudaSetDevice(ctx->device));
   return nq_comm_attach(ctx, handles);
 }
+
+int nqmc_comm_active(const nqmc_ctx* ctx) { return ctx && nq_comm_active(ctx) ? 1 : 0; }
 
 int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream st) {
   if (!ctx) return NQMC_ERR_ARG;

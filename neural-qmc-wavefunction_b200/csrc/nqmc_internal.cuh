@@ -25,6 +25,13 @@ struct MlpOff {     // one Dense(F,H)-tanh-Dense(H,H)-tanh-Dense(H,1) network
   int b1, W1, b2, W2, b3, W3;
 };
 
+#define NQMC_SIMPLE_MAX_HIDDEN 6
+struct SimpleNet {  // kind 0: Dense(dim[0],dim[1])-act-...-Dense(dim[n_hidden],1); dim[0] = 3N
+  int n_hidden, act;
+  int dim[NQMC_SIMPLE_MAX_HIDDEN + 1];
+  int offW[NQMC_SIMPLE_MAX_HIDDEN + 1], offb[NQMC_SIMPLE_MAX_HIDDEN + 1];   // entry n_hidden = output layer
+};
+
 struct DevSys {     // passed by value to kernels (<= 4 KB kernel-parameter budget)
   int A, N, n_up, n_dn;
   int kind, H, use_cusp, use_bf;
@@ -40,7 +47,7 @@ struct DevSys {     // passed by value to kernels (<= 4 KB kernel-parameter budg
   int ee_cusp_b;
   int en_cusp_b0[NQMC_MAX_ATOMS], en_cusp_W0[NQMC_MAX_ATOMS], en_cusp_b1[NQMC_MAX_ATOMS], en_cusp_W1[NQMC_MAX_ATOMS];
   MlpOff bf;                   // backflow eta network (F=2, H=16)
-  MlpOff simple;               // kind 0 network
+  SimpleNet simple;            // kind 0 network
   MlpOff mlp[NQMC_MAX_MLP];    // m < n_up: spin-up orbital m ; else spin-down orbital m - n_up
 };
 
@@ -92,6 +99,7 @@ struct nqmc_ctx {
   double* hdr_tmp = nullptr;   // [8]
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
+  const float* sigma_dev = nullptr;       // device-resident proposal width (set by nqmc_sample while it runs)
   // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
   bool prof_on = false;
   static constexpr int PROF_KINDS = 6, PROF_RING = 512;
@@ -225,6 +233,8 @@ int nq_comm_attach(nqmc_ctx* ctx, const void* handles);
 int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st);
 bool nq_comm_active(const nqmc_ctx* ctx);
 void nq_comm_free(nqmc_ctx* ctx);
+int nq_adapt_sigma(nqmc_ctx* ctx, float* n_acc, int64_t W, int steps, float target, float gain, float* sigma_dev,
+                   cudaStream_t st);
 int nq_aos_soa(nqmc_ctx* ctx, const float* src, float* dst, int64_t W, bool to_soa, cudaStream_t st);
 int nq_rng_fill(nqmc_ctx* ctx, uint64_t seed, uint64_t step, int64_t wid0, int64_t W, float* normals, float* uniforms,
                 cudaStream_t st);

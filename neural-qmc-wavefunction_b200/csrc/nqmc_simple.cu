@@ -1,50 +1,39 @@
 // nqmc_simple.cu -- ansatz kind 0: the reference's only *implemented* wavefunction,
 //   log|psi| = MLP(flatten r) + sum_i log sum_A exp(-alpha |r_i - R_A|)
-// (src/nqmc/wavefunction/simple.py:41-70 SimpleMLP, :124-164 envelope + __call__), used by BASELINE
-// config 1 (H2, scripts/train_h2.py).  It is the plumbing case (32 chains), so the mapping is
-// simple: one WARP per walker, lanes across hidden units, weights staged once per CTA in shared
-// memory; the forward-Laplacian carries the D = 3N input tangents explicitly
-// (hamiltonian/molecular.py:52-69 computes the same trace + |grad|^2 by nested autodiff).
+// (src/nqmc/wavefunction/simple.py:41-70 SimpleMLP -- any tuple of hidden widths, 'tanh' or 'silu' --
+// and :124-164 envelope + __call__), used by BASELINE config 1 (H2, scripts/train_h2.py).
+// It is the plumbing case (32 chains), so the mapping is simple: one WARP per walker, lanes across the
+// units of a layer, all weights staged once per CTA in shared memory.  The forward Laplacian carries the
+// D = 3N input tangents explicitly through every layer (value v, tangents G[d], Laplacian L):
+//   u = W^T v + b ; Gu[d] = W^T G[d] ; Lu = W^T L
+//   v' = s(u) ; G'[d] = s'(u) Gu[d] ; L' = s'(u) Lu + s''(u) sum_d Gu[d]^2
+// (hamiltonian/molecular.py:52-69 obtains the same trace + |grad|^2 from a dense nested-autodiff Hessian).
 #include "nqmc_internal.cuh"
 
 namespace {
 
 constexpr int SW = 4;            // warps (walkers in flight) per CTA
-constexpr int MAXH = 128;
-constexpr int MAXD = 48;
-constexpr int HPL = MAXH / 32;   // hidden units per lane
+constexpr int MAXD = 48;         // 3 * NQMC_MAX_ELEC
+constexpr int DCH = 8;           // tangents accumulated per pass over a weight column
 
-struct SimpleSmem {
-  float* W1;   // [D][H0]
-  float* W2;   // [H0][H1]
-  float* b1;   // [H0]
-  float* b2;   // [H1]
-  float* W3;   // [H1]
-  float* scr;  // per warp: h1[H0], lh1[H0], G1[D][H0], x[D], d2[H1]
-};
-
-__device__ __forceinline__ SimpleSmem carve(float* base, int D, int H0, int H1, int warp) {
-  SimpleSmem s;
-  s.W1 = base;
-  s.W2 = s.W1 + D * H0;
-  s.b1 = s.W2 + H0 * H1;
-  s.b2 = s.b1 + H0;
-  s.W3 = s.b2 + H1;
-  const int per_warp = 2 * H0 + D * H0 + MAXD + H1;
-  s.scr = s.W3 + H1 + warp * per_warp;
-  return s;
+__device__ __forceinline__ void act_rules(const int act, const float u, float& h, float& a1, float& a2) {
+  if (act == NQMC_ACT_TANH) {
+    h = nq_tanh(u);
+    a1 = fmaf(-h, h, 1.f);
+    a2 = -2.f * h * a1;
+  } else {   // silu: u * sigmoid(u)
+    const float s = 1.0f / (1.0f + __expf(-u));
+    h = u * s;
+    a1 = s * fmaf(u, 1.0f - s, 1.0f);
+    a2 = s * (1.0f - s) * fmaf(u, 1.0f - 2.0f * s, 2.0f);
+  }
 }
 
-__device__ __forceinline__ void stage_weights(const DevSys& s, const float* __restrict__ theta, const SimpleSmem& m,
-                                              int D, int H0, int H1) {
-  const MlpOff o = s.simple;
-  for (int i = threadIdx.x; i < D * H0; i += blockDim.x) m.W1[i] = theta[o.W1 + i];
-  for (int i = threadIdx.x; i < H0 * H1; i += blockDim.x) m.W2[i] = theta[o.W2 + i];
-  for (int i = threadIdx.x; i < H0; i += blockDim.x) m.b1[i] = theta[o.b1 + i];
-  for (int i = threadIdx.x; i < H1; i += blockDim.x) { m.b2[i] = theta[o.b2 + i]; m.W3[i] = theta[o.W3 + i]; }
+__device__ __forceinline__ void stage_theta(const DevSys& s, const float* __restrict__ theta, float* sh) {
+  for (int i = threadIdx.x; i < s.P; i += blockDim.x) sh[i] = theta[i];
 }
 
-// envelope: value, gradient (per lane: one electron-axis each), Laplacian -- done by lane 0..D-1
+// envelope of electron i: value, gradient, Laplacian of log sum_A exp(-alpha d_iA)
 __device__ __forceinline__ void envelope(const DevSys& s, const float* x, int i, float& val, float& gx, float& gy,
                                          float& gz, float& lap) {
   float S = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
@@ -65,58 +54,91 @@ __device__ __forceinline__ void envelope(const DevSys& s, const float* x, int i,
   lap = sl * iS - (gx * gx + gy * gy + gz * gz);
 }
 
+// per-warp scratch of the evaluation kernel: two buffers [D + 2][HM] (row 0 value, 1..D tangents, D+1 Laplacian)
+// + x[MAXD].  HM = widest layer (>= D).
+__host__ __device__ inline int simple_hm(const DevSys& s) {
+  int hm = 3 * s.N;
+  for (int l = 1; l <= s.simple.n_hidden; ++l) hm = s.simple.dim[l] > hm ? s.simple.dim[l] : hm;
+  return hm;
+}
+
 // mode 0: log|psi| ; mode 1: local energy
 __global__ void __launch_bounds__(SW * 32) simple_eval_kernel(const DevSys s, const float* __restrict__ theta,
                                                               const float* __restrict__ r, const int64_t W,
                                                               float* __restrict__ logabs, float* __restrict__ e_l,
                                                               float* __restrict__ parts, const int mode) {
   extern __shared__ __align__(16) float smem[];
-  const int D = 3 * s.N, H0 = s.H, H1 = s.H;
+  const int D = 3 * s.N, HM = simple_hm(s), NH = s.simple.n_hidden, act = s.simple.act;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SimpleSmem m = carve(smem, D, H0, H1, warp);
-  stage_weights(s, theta, m, D, H0, H1);
+  float* th = smem;
+  const int rows = mode == 1 ? D + 2 : 1;
+  float* buf0 = smem + s.P + warp * (2 * rows * HM + MAXD);
+  float* buf1 = buf0 + rows * HM;
+  float* x = buf1 + rows * HM;
+  stage_theta(s, theta, th);
   __syncthreads();
-  float* h1 = m.scr;
-  float* lh1 = h1 + H0;
-  float* G1 = lh1 + H0;
-  float* x = G1 + D * H0;
-  const float b3 = theta[s.simple.b3];
   for (int64_t w = (int64_t)blockIdx.x * SW + warp; w < W; w += (int64_t)gridDim.x * SW) {
     for (int d = lane; d < D; d += 32) x[d] = r[(int64_t)d * W + w];
     __syncwarp();
-    // layer 1
-    for (int j = lane; j < H0; j += 32) {
-      float u = m.b1[j], w2 = 0.f;
-      for (int d = 0; d < D; ++d) { float wv = m.W1[d * H0 + j]; u = fmaf(wv, x[d], u); w2 = fmaf(wv, wv, w2); }
-      float h = nq_tanh(u), tp = fmaf(-h, h, 1.f);
-      h1[j] = h;
+    float* in = buf0;
+    float* out = buf1;
+    // input "layer": v = x, G = identity, L = 0
+    for (int k = lane; k < D; k += 32) {
+      in[k] = x[k];
       if (mode == 1) {
-        lh1[j] = -2.f * h * tp * w2;
-        for (int d = 0; d < D; ++d) G1[d * H0 + j] = tp * m.W1[d * H0 + j];
+        for (int d = 0; d < D; ++d) in[(1 + d) * HM + k] = d == k ? 1.f : 0.f;
+        in[(D + 1) * HM + k] = 0.f;
       }
     }
     __syncwarp();
-    // layer 2 + output: lane owns hidden units k = lane + 32 t (static slots)
-    float val = 0.f;
-    float hk[HPL], tpk[HPL], w3k[HPL], luk[HPL], g2k[HPL];
-#pragma unroll
-    for (int t = 0; t < HPL; ++t) {
-      const int k = lane + 32 * t;
-      hk[t] = tpk[t] = w3k[t] = luk[t] = g2k[t] = 0.f;
-      if (k < H1) {
-        float u = m.b2[k], lu = 0.f;
-        for (int j = 0; j < H0; ++j) {
-          float wv = m.W2[j * H1 + k];
-          u = fmaf(wv, h1[j], u);
-          if (mode == 1) lu = fmaf(wv, lh1[j], lu);
+    for (int l = 0; l < NH; ++l) {
+      const int K = s.simple.dim[l], M = s.simple.dim[l + 1];
+      const float* Wl = th + s.simple.offW[l];
+      const float* bl = th + s.simple.offb[l];
+      for (int j = lane; j < M; j += 32) {
+        float u = bl[j], lu = 0.f;
+        for (int k = 0; k < K; ++k) {
+          const float wv = Wl[k * M + j];
+          u = fmaf(wv, in[k], u);
+          if (mode == 1) lu = fmaf(wv, in[(D + 1) * HM + k], lu);
         }
-        float h = nq_tanh(u);
-        hk[t] = h; tpk[t] = fmaf(-h, h, 1.f); w3k[t] = m.W3[k]; luk[t] = lu;
-        val = fmaf(w3k[t], h, val);
+        float h, a1, a2;
+        act_rules(act, u, h, a1, a2);
+        out[j] = h;
+        if (mode == 1) {
+          float g2 = 0.f;
+          for (int d0 = 0; d0 < D; d0 += DCH) {
+            float acc[DCH];
+#pragma unroll
+            for (int dd = 0; dd < DCH; ++dd) acc[dd] = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const float wv = Wl[k * M + j];
+#pragma unroll
+              for (int dd = 0; dd < DCH; ++dd)
+                if (d0 + dd < D) acc[dd] = fmaf(wv, in[(1 + d0 + dd) * HM + k], acc[dd]);
+            }
+#pragma unroll
+            for (int dd = 0; dd < DCH; ++dd)
+              if (d0 + dd < D) {
+                g2 = fmaf(acc[dd], acc[dd], g2);
+                out[(1 + d0 + dd) * HM + j] = a1 * acc[dd];
+              }
+          }
+          out[(D + 1) * HM + j] = fmaf(a1, lu, a2 * g2);
+        }
       }
+      __syncwarp();
+      float* t = in; in = out; out = t;
     }
-    val = warp_sum(val) + b3;
-    // envelope (lanes < N)
+    // output layer Dense(1)
+    const int K = s.simple.dim[NH];
+    const float* Wo = th + s.simple.offW[NH];
+    float val = 0.f, lap = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      val = fmaf(Wo[k], in[k], val);
+      if (mode == 1) lap = fmaf(Wo[k], in[(D + 1) * HM + k], lap);
+    }
+    val = warp_sum(val) + th[s.simple.offb[NH]];
     float env = 0.f, egx = 0.f, egy = 0.f, egz = 0.f, elap = 0.f;
     if (lane < s.N) envelope(s, x, lane, env, egx, egy, egz, elap);
     const float envsum = warp_sum(env);
@@ -124,27 +146,14 @@ __global__ void __launch_bounds__(SW * 32) simple_eval_kernel(const DevSys s, co
       if (lane == 0) logabs[w] = val + envsum;
     } else {
       float g2 = 0.f;
-#pragma unroll 1
       for (int d = 0; d < D; ++d) {
-        float gpart = 0.f;
-#pragma unroll
-        for (int t = 0; t < HPL; ++t) {
-          const int k = lane + 32 * t;
-          if (k < H1) {
-            float gu = 0.f;
-            for (int j = 0; j < H0; ++j) gu = fmaf(m.W2[j * H1 + k], G1[d * H0 + j], gu);
-            g2k[t] = fmaf(gu, gu, g2k[t]);
-            gpart = fmaf(w3k[t] * tpk[t], gu, gpart);
-          }
-        }
-        const float gm = warp_sum(gpart);
+        float gp = 0.f;
+        for (int k = lane; k < K; k += 32) gp = fmaf(Wo[k], in[(1 + d) * HM + k], gp);
+        const float gm = warp_sum(gp);
         const int i = d / 3, ax = d % 3;
         const float ge = __shfl_sync(0xffffffffu, ax == 0 ? egx : (ax == 1 ? egy : egz), i);
         g2 = fmaf(gm + ge, gm + ge, g2);
       }
-      float lap = 0.f;
-#pragma unroll
-      for (int t = 0; t < HPL; ++t) lap = fmaf(w3k[t], fmaf(tpk[t], luk[t], -2.f * hk[t] * tpk[t] * g2k[t]), lap);
       lap = warp_sum(lap) + warp_sum(elap);
       // potentials (molecular.py:87-135), lanes split the pairs
       float ven = 0.f, vee = 0.f;
@@ -173,68 +182,90 @@ __global__ void __launch_bounds__(SW * 32) simple_eval_kernel(const DevSys s, co
   }
 }
 
-// weighted parameter gradient, kind 0.  Block accumulator in shared memory, flushed to a slab.
+// weighted parameter gradient, kind 0.  Block accumulator in shared memory, flushed to a per-CTA slab.
+// per-warp scratch: h[l] (inputs of every layer) and a1[l] (activation derivative), total 2 * sum(dim), + delta[2][HM].
+__host__ __device__ inline int simple_act_floats(const DevSys& s) {
+  int n = 0;
+  for (int l = 0; l <= s.simple.n_hidden; ++l) n += s.simple.dim[l];
+  return n;
+}
+
 __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, const float* __restrict__ theta,
                                                               const float* __restrict__ r, const float* __restrict__ wgt,
                                                               const double* __restrict__ hdr,
                                                               const float* __restrict__ e_l, const int64_t W,
                                                               float* __restrict__ part) {
   extern __shared__ __align__(16) float smem[];
-  const int D = 3 * s.N, H0 = s.H, H1 = s.H;
+  const int HM = simple_hm(s), NH = s.simple.n_hidden, act = s.simple.act, NA = simple_act_floats(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SimpleSmem m = carve(smem, D, H0, H1, warp);
-  const int per_warp = 2 * H0 + D * H0 + MAXD + H1;
-  float* acc = m.W3 + H1 + SW * per_warp;      // [P] in theta-relative order of the network block
   const int P = s.P;
-  stage_weights(s, theta, m, D, H0, H1);
+  float* th = smem;
+  float* acc = smem + P;
+  float* hbuf = acc + P + warp * (2 * NA + 2 * HM);
+  float* abuf = hbuf + NA;
+  float* dl0 = abuf + NA;
+  float* dl1 = dl0 + HM;
+  stage_theta(s, theta, th);
   for (int i = threadIdx.x; i < P; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
-  float* h1 = m.scr;
-  float* d1 = h1 + H0;
-  float* x = h1 + 2 * H0 + D * H0;
-  float* d2 = x + MAXD;
-  const MlpOff o = s.simple;
   float center = 0.f;
   if (hdr) center = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
   for (int64_t w = (int64_t)blockIdx.x * SW + warp; w < W; w += (int64_t)gridDim.x * SW) {
     float wt = 1.f;
     if (wgt) wt = wgt[w];
     else if (e_l) { float e = e_l[w]; wt = isfinite(e) ? e - center : 0.f; }
-    for (int d = lane; d < D; d += 32) x[d] = r[(int64_t)d * W + w];
+    const int D = s.simple.dim[0];
+    for (int d = lane; d < D; d += 32) hbuf[d] = r[(int64_t)d * W + w];
     __syncwarp();
-    for (int j = lane; j < H0; j += 32) {
-      float u = m.b1[j];
-      for (int d = 0; d < D; ++d) u = fmaf(m.W1[d * H0 + j], x[d], u);
-      h1[j] = nq_tanh(u);
-    }
-    __syncwarp();
-    for (int k = lane; k < H1; k += 32) {
-      float u = m.b2[k];
-      for (int j = 0; j < H0; ++j) u = fmaf(m.W2[j * H1 + k], h1[j], u);
-      float h = nq_tanh(u);
-      atomicAdd(&acc[o.W3 + k], wt * h);
-      float dd = wt * m.W3[k] * fmaf(-h, h, 1.f);
-      d2[k] = dd;
-      atomicAdd(&acc[o.b2 + k], dd);
-    }
-    if (lane == 0) atomicAdd(&acc[o.b3], wt);
-    __syncwarp();
-    for (int j = lane; j < H0; j += 32) {
-      float sacc = 0.f;
-      const float hj = h1[j];
-      for (int k = 0; k < H1; ++k) {
-        sacc = fmaf(m.W2[j * H1 + k], d2[k], sacc);
+    int off = 0;
+    for (int l = 0; l < NH; ++l) {           // forward, keeping every layer's input and s'(u)
+      const int K = s.simple.dim[l], M = s.simple.dim[l + 1];
+      const float* Wl = th + s.simple.offW[l];
+      const float* bl = th + s.simple.offb[l];
+      const float* in = hbuf + off;
+      for (int j = lane; j < M; j += 32) {
+        float u = bl[j];
+        for (int k = 0; k < K; ++k) u = fmaf(Wl[k * M + j], in[k], u);
+        float h, a1, a2;
+        act_rules(act, u, h, a1, a2);
+        hbuf[off + K + j] = h;
+        abuf[off + K + j] = a1;
       }
-      const float dj = sacc * fmaf(-hj, hj, 1.f);
-      d1[j] = dj;
-      atomicAdd(&acc[o.b1 + j], dj);
-      for (int d = 0; d < D; ++d) atomicAdd(&acc[o.W1 + d * H0 + j], x[d] * dj);
+      off += K;
+      __syncwarp();
     }
-    __syncwarp();
-    // dW2[j][k] += h1[j] * d2[k]: lanes over k (coalesced shared atomics)
-    for (int j = 0; j < H0; ++j) {
-      const float hj = h1[j];
-      for (int k = lane; k < H1; k += 32) atomicAdd(&acc[o.W2 + j * H1 + k], hj * d2[k]);
+    // output layer: d/dW_out = wt * h_last, d/db_out = wt ; delta_last = wt * W_out * s'(u_last)
+    {
+      const int K = s.simple.dim[NH];
+      const float* Wo = th + s.simple.offW[NH];
+      for (int k = lane; k < K; k += 32) {
+        atomicAdd(&acc[s.simple.offW[NH] + k], wt * hbuf[off + k]);
+        dl0[k] = wt * Wo[k] * (NH > 0 ? abuf[off + k] : 1.f);
+      }
+      if (lane == 0) atomicAdd(&acc[s.simple.offb[NH]], wt);
+      __syncwarp();
+    }
+    float* dcur = dl0;
+    float* dnext = dl1;
+    for (int l = NH - 1; l >= 0; --l) {      // reverse
+      const int K = s.simple.dim[l], M = s.simple.dim[l + 1];
+      off -= K;
+      const float* Wl = th + s.simple.offW[l];
+      const float* in = hbuf + off;
+      for (int j = lane; j < M; j += 32) atomicAdd(&acc[s.simple.offb[l] + j], dcur[j]);
+      for (int k = 0; k < K; ++k) {           // dW[k][j] += in[k] * delta[j]: lanes over j (conflict-free atomics)
+        const float hk = in[k];
+        for (int j = lane; j < M; j += 32) atomicAdd(&acc[s.simple.offW[l] + k * M + j], hk * dcur[j]);
+      }
+      if (l > 0) {
+        for (int k = lane; k < K; k += 32) {
+          float sacc = 0.f;
+          for (int j = 0; j < M; ++j) sacc = fmaf(Wl[k * M + j], dcur[j], sacc);
+          dnext[k] = sacc * abuf[off + k];
+        }
+      }
+      __syncwarp();
+      float* t = dcur; dcur = dnext; dnext = t;
     }
     __syncwarp();
   }
@@ -251,11 +282,12 @@ __global__ void simple_grad_finish_kernel(const float* __restrict__ part, const 
   out[i] = a;
 }
 
-size_t simple_smem_bytes(const DevSys& s, bool with_acc) {
-  const int D = 3 * s.N, H0 = s.H, H1 = s.H;
-  size_t f = (size_t)D * H0 + (size_t)H0 * H1 + H0 + 2 * H1 + (size_t)SW * (2 * H0 + D * H0 + MAXD + H1);
-  if (with_acc) f += s.P;
-  return f * sizeof(float);
+size_t simple_eval_smem(const DevSys& s, int mode) {
+  const int rows = mode == 1 ? 3 * s.N + 2 : 1;
+  return ((size_t)s.P + (size_t)SW * (2 * rows * simple_hm(s) + MAXD)) * sizeof(float);
+}
+size_t simple_grad_smem(const DevSys& s) {
+  return (2 * (size_t)s.P + (size_t)SW * (2 * simple_act_floats(s) + 2 * simple_hm(s))) * sizeof(float);
 }
 
 }  // namespace
@@ -263,11 +295,11 @@ size_t simple_smem_bytes(const DevSys& s, bool with_acc) {
 static int simple_launch_eval(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, float* e_l, float* parts,
                               int mode, cudaStream_t st) {
   const DevSys& s = ctx->sys;
-  if (s.H > MAXH || 3 * s.N > MAXD) {
-    ctx->err = "SimpleWavefunction: hidden width > 128 or more than 16 electrons";
+  const size_t smem = simple_eval_smem(s, mode);
+  if (smem > 227 * 1024) {
+    ctx->err = "SimpleWavefunction: network + per-walker tangent scratch exceed 227 KB of shared memory";
     return NQMC_ERR_UNSUPPORTED;
   }
-  const size_t smem = simple_smem_bytes(s, false);
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
@@ -290,7 +322,7 @@ int nq_simple_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float
 int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                     int64_t W, double* out, cudaStream_t st) {
   const DevSys& s = ctx->sys;
-  const size_t smem = simple_smem_bytes(s, true);
+  const size_t smem = simple_grad_smem(s);
   if (smem > 227 * 1024) {
     ctx->err = "SimpleWavefunction gradient: parameter block does not fit in shared memory";
     return NQMC_ERR_UNSUPPORTED;

@@ -372,12 +372,13 @@ __global__ void jastrow_from_sums_kernel(const DevSys s, const double* __restric
 // ---------------------------------------------------------------------------------------------
 // proposal: r' = r + sigma * n   (metropolis.py:119-121)
 __global__ void propose_kernel(const DevSys s, const float* __restrict__ r, const float* __restrict__ normals,
-                               const uint64_t seed, const uint64_t step, const int64_t wid0, const float sigma,
-                               const int64_t W, float* __restrict__ r_prop) {
+                               const uint64_t seed, const uint64_t step, const int64_t wid0, const float sigma_arg,
+                               const float* __restrict__ sigma_dev, const int64_t W, float* __restrict__ r_prop) {
   nq_pdl_trigger();                                    // the value pass behind this kernel may start staging its weights
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   const int nn = 3 * s.N;
+  const float sigma = sigma_dev ? *sigma_dev : sigma_arg;   // device-resident step size (adaptive burn-in)
   if (normals != nullptr) {
     for (int c = 0; c < nn; ++c) r_prop[(int64_t)c * W + w] = fmaf(sigma, normals[(int64_t)c * W + w], r[(int64_t)c * W + w]);
   } else {
@@ -727,7 +728,35 @@ int dispatch_ns(nqmc_ctx* ctx, F&& f) {
 
 int nq_launch_propose(nqmc_ctx* ctx, const float* r, const float* normals, uint64_t seed, uint64_t step, int64_t wid0,
                       float sigma, int64_t W, float* r_prop, cudaStream_t st) {
-  propose_kernel<<<(unsigned)((W + 255) / 256), 256, 0, st>>>(ctx->sys, r, normals, seed, step, wid0, sigma, W, r_prop);
+  propose_kernel<<<(unsigned)((W + 255) / 256), 256, 0, st>>>(ctx->sys, r, normals, seed, step, wid0, sigma,
+                                                              ctx->sigma_dev, W, r_prop);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
+// Adaptive proposal width (the reference declares target_acceptance / adapt_step at
+// src/nqmc/sampler/metropolis.py:52-54 and never reads them): after a block of `steps` burn-in moves,
+//   sigma <- sigma * exp(gain * (acceptance - target)),   clamped to [1e-3, 10] bohr,
+// with the block's acceptance taken from the per-walker counters, which are zeroed for the next block.
+__global__ void __launch_bounds__(1024) adapt_sigma_kernel(float* __restrict__ n_acc, const int64_t W, const float steps,
+                                                           const float target, const float gain, float* __restrict__ sigma) {
+  __shared__ double sh[32];
+  double a = 0;
+  for (int64_t w = threadIdx.x; w < W; w += blockDim.x) { a += (double)n_acc[w]; n_acc[w] = 0.f; }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    const float acc = (float)(t / ((double)W * steps));
+    *sigma = fminf(fmaxf(*sigma * __expf(gain * (acc - target)), 1e-3f), 10.0f);
+  }
+}
+
+int nq_adapt_sigma(nqmc_ctx* ctx, float* n_acc, int64_t W, int steps, float target, float gain, float* sigma_dev,
+                   cudaStream_t st) {
+  adapt_sigma_kernel<<<1, 1024, 0, st>>>(n_acc, W, (float)steps, target, gain, sigma_dev);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }

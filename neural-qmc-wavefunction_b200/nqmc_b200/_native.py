@@ -1,14 +1,16 @@
-"""ctypes binding of libnqmc_b200.so (include/nqmc_b200.h) and the device-side Context.
+"""ctypes binding of libnqmc_b200.so (include/nqmc_b200.h), device buffers, and the device-side Context.
 
-PyTorch is used here for plumbing only: device buffers (``torch.empty(..., device='cuda')``),
-the current CUDA stream handle and, in nqmc_b200.parallel, ``torch.distributed``.  Every
-computation on walkers goes through the C ABI.  There is no CPU fallback: if the shared library
-or a CUDA device is missing, construction raises.
+No PyTorch, no JAX: device memory, pinned host memory and streams come from the library itself
+(``nqmc_dev_alloc`` ...), wrapped by ``DeviceArray``.  Anything that exposes ``data_ptr()`` (a torch CUDA tensor in
+the tests, an XLA buffer behind the FFI shim) is accepted wherever a device buffer is expected.  Every computation
+on walkers goes through the C ABI.  There is no CPU fallback: if the shared library or a CUDA device is missing,
+construction raises.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -18,6 +20,7 @@ _lib = None
 
 KIND_SIMPLE = 0
 KIND_ANTISYMMETRIC = 1
+ACTIVATIONS = {"tanh": 0, "silu": 1}
 HDR_N, HDR_SUM_E, HDR_SUM_E2, HDR_N_ACCEPT, HDR_N_BAD, HDR_SIZE = 0, 1, 2, 3, 4, 8
 
 EXPORTS = [
@@ -26,7 +29,10 @@ EXPORTS = [
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
     "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
-    "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce",
+    "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample",
+    "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
+    "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync",
+    "nqmc_mem_last_error",
 ]
 
 
@@ -42,7 +48,8 @@ class _System(C.Structure):
 class _Net(C.Structure):
     _fields_ = [("kind", C.c_int32), ("hidden0", C.c_int32), ("hidden1", C.c_int32), ("use_cusp", C.c_int32),
                 ("use_backflow", C.c_int32), ("_pad", C.c_int32), ("envelope_decay", C.c_double),
-                ("cusp_same", C.c_double), ("cusp_diff", C.c_double)]
+                ("cusp_same", C.c_double), ("cusp_diff", C.c_double),
+                ("n_hidden", C.c_int32), ("activation", C.c_int32), ("hidden", C.c_int32 * 6)]
 
 
 def lib_path() -> str:
@@ -94,31 +101,216 @@ def load_library():
     lib.nqmc_comm_create.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.nqmc_comm_attach.argtypes = [vp, vp]
     lib.nqmc_comm_allreduce.argtypes = [vp, vp, i64, vp]
+    lib.nqmc_comm_active.argtypes = [vp]
+    lib.nqmc_sample.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, i64, i64, i64, vp, vp, vp, f32, i64, vp]
+    sz = C.c_size_t
+    lib.nqmc_device_count.argtypes = []
+    lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
+    lib.nqmc_dev_free.argtypes = [C.c_int, vp]
+    lib.nqmc_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.nqmc_host_free.argtypes = [vp]
+    lib.nqmc_dev_memcpy.argtypes = [C.c_int, vp, vp, sz, C.c_int, vp]
+    lib.nqmc_dev_copy_rows.argtypes = [C.c_int, vp, sz, vp, sz, sz, sz, vp]
+    lib.nqmc_dev_memset.argtypes = [C.c_int, vp, C.c_int, sz, vp]
+    lib.nqmc_stream_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.nqmc_stream_destroy.argtypes = [C.c_int, vp]
+    lib.nqmc_stream_sync.argtypes = [C.c_int, vp]
+    lib.nqmc_mem_last_error.argtypes = []
+    lib.nqmc_mem_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 
 
-def _torch():
-    import torch
-    return torch
+def _mem_check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {load_library().nqmc_mem_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(load_library().nqmc_device_count())
+
+
+def default_device() -> int:
+    """The device a new Context / DeviceArray lands on when none is given: NQMC_DEVICE, else LOCAL_RANK (one
+    process per GPU under torchrun / mpirun), else the current torch device if the CALLER has already imported
+    torch and initialised CUDA (never imported from here), else 0."""
+    for var in ("NQMC_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(var, "") != "":
+            return int(os.environ[var])
+    t = sys.modules.get("torch")
+    if t is not None:
+        try:
+            if t.cuda.is_initialized():
+                return int(t.cuda.current_device())
+        except Exception:
+            pass
+    return 0
+
+
+class _HostView(np.ndarray):
+    """ndarray that also answers ``.numpy()`` / ``.cpu()`` so results read the same whether a caller holds a
+    DeviceArray or (in the tests) a torch tensor."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+    def cpu(self):
+        return self
+
+    def item(self, *a):
+        return np.asarray(self).item(*a)
+
+
+class DeviceArray:
+    """A caller-owned buffer in device memory (nqmc_dev_alloc).  Row-major, fixed dtype/shape; views share the
+    allocation.  ``numpy()`` copies back (synchronising the stream); ``data_ptr()`` is what the C ABI takes."""
+
+    __slots__ = ("ptr", "shape", "dtype", "device", "_base", "_owns", "__weakref__")
+
+    def __init__(self, shape, dtype=np.float32, device: Optional[int] = None, _ptr: Optional[int] = None, _base=None):
+        self.shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        self.device = default_device() if device is None else int(device)
+        self._base = _base
+        if _ptr is None:
+            p = C.c_void_p()
+            _mem_check(load_library().nqmc_dev_alloc(self.device, self.nbytes, C.byref(p)), "nqmc_dev_alloc")
+            self.ptr, self._owns = int(p.value), True
+        else:
+            self.ptr, self._owns = int(_ptr), False
+
+    def __del__(self):
+        try:
+            if self._owns and self.ptr and _lib is not None:
+                _lib.nqmc_dev_free(self.device, self.ptr)
+                self.ptr = 0
+        except Exception:
+            pass
+
+    # -- geometry
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    @property
+    def nbytes(self) -> int:
+        return self.size * self.dtype.itemsize
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def numel(self) -> int:
+        return self.size
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def view(self, *shape) -> "DeviceArray":
+        shape = shape[0] if len(shape) == 1 and not np.isscalar(shape[0]) else shape
+        shape = list(shape)
+        if -1 in shape:
+            k = shape.index(-1)
+            shape[k] = self.size // max(1, -int(np.prod(shape)))
+        if int(np.prod(shape)) != self.size:
+            raise ValueError(f"cannot view {self.shape} as {tuple(shape)}")
+        return DeviceArray(shape, self.dtype, self.device, _ptr=self.ptr, _base=self)
+
+    reshape = view
+
+    def row(self, i: int) -> "DeviceArray":
+        """View of ``self[i]`` (leading index)."""
+        if not 0 <= i < self.shape[0]:
+            raise IndexError(i)
+        inner = self.shape[1:]
+        step = (int(np.prod(inner)) if inner else 1) * self.dtype.itemsize
+        return DeviceArray(inner, self.dtype, self.device, _ptr=self.ptr + i * step, _base=self)
+
+    # -- transfers
+    def copy_from_host(self, a, stream: int = 0) -> "DeviceArray":
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        if a.size != self.size:
+            raise ValueError(f"host array has {a.size} elements, device buffer {self.size}")
+        lib = load_library()
+        _mem_check(lib.nqmc_dev_memcpy(self.device, self.ptr, a.ctypes.data, self.nbytes, 1, stream), "nqmc_dev_memcpy")
+        _mem_check(lib.nqmc_stream_sync(self.device, stream), "nqmc_stream_sync")      # `a` may be a temporary
+        return self
+
+    def copy_from(self, other, stream: int = 0) -> "DeviceArray":
+        """device -> device from anything with data_ptr() holding at least nbytes."""
+        _mem_check(load_library().nqmc_dev_memcpy(self.device, self.ptr, _ptr(other), self.nbytes, 3, stream),
+                   "nqmc_dev_memcpy")
+        return self
+
+    def zero_(self, stream: int = 0) -> "DeviceArray":
+        _mem_check(load_library().nqmc_dev_memset(self.device, self.ptr, 0, self.nbytes, stream), "nqmc_dev_memset")
+        return self
+
+    def numpy(self, stream: int = 0) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        lib = load_library()
+        _mem_check(lib.nqmc_dev_memcpy(self.device, out.ctypes.data, self.ptr, self.nbytes, 2, stream), "nqmc_dev_memcpy")
+        _mem_check(lib.nqmc_stream_sync(self.device, stream), "nqmc_stream_sync")
+        return out
+
+    def cpu(self) -> _HostView:
+        return self.numpy().view(_HostView)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def clone(self, stream: int = 0) -> "DeviceArray":
+        return DeviceArray(self.shape, self.dtype, self.device).copy_from(self, stream)
+
+    def contiguous(self):
+        return self
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, device={self.device}, ptr=0x{self.ptr:x})"
+
+
+def to_device(a, dtype=np.float32, device: Optional[int] = None, stream: int = 0):
+    """numpy -> new DeviceArray; device buffers (anything with data_ptr()) pass through untouched."""
+    if a is None or hasattr(a, "data_ptr"):
+        return a
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return DeviceArray(a.shape, dtype, device).copy_from_host(a, stream)
 
 
 def _ptr(t) -> Optional[int]:
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _shape(t):
+    return tuple(t.shape)
 
 
 class Context:
-    """One (geometry, network shape) on one GPU.  Thin, stateful wrapper over nqmc_ctx."""
+    """One (geometry, network shape) on one GPU.  Thin, stateful wrapper over nqmc_ctx.
+    ``stream``: a cudaStream_t handle (int) every call is issued on; 0 = the legacy default stream, which is also
+    what torch uses unless told otherwise, so tests that mix torch tensors with this class stay ordered."""
 
     def __init__(self, R: np.ndarray, Z: np.ndarray, n_up: int, n_dn: int, v_nn: float, kind: int,
-                 hidden: Tuple[int, int], use_cusp: bool = False, use_backflow: bool = False,
+                 hidden: Tuple[int, ...], use_cusp: bool = False, use_backflow: bool = False,
                  envelope_decay: float = 1.0, cusp_same: float = 0.5, cusp_diff: float = 0.25,
-                 device: Optional[int] = None):
-        torch = _torch()
+                 device: Optional[int] = None, activation: str = "tanh", stream: int = 0):
         self.lib = load_library()
-        if not torch.cuda.is_available():
+        if device_count() <= 0:
             raise NativeError("no CUDA device is visible; the nqmc_b200 walker loop has no CPU fallback")
-        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.device = default_device() if device is None else int(device)
+        self.stream = int(stream)
         self._R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 3)
         self._Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1)
         self.n_atoms, self.n_up, self.n_dn = self._R.shape[0], int(n_up), int(n_dn)
@@ -127,8 +319,18 @@ class Context:
         sysm = _System(self.n_atoms, self.n_elec, self.n_up, 0,
                        self._R.ctypes.data_as(C.POINTER(C.c_double)), self._Z.ctypes.data_as(C.POINTER(C.c_double)),
                        float(v_nn))
-        net = _Net(kind, int(hidden[0]), int(hidden[1]), int(bool(use_cusp)), int(bool(use_backflow)), 0,
-                   float(envelope_decay), float(cusp_same), float(cusp_diff))
+        if activation not in ACTIVATIONS:
+            raise ValueError(f"Unknown activation: {activation}")          # simple.py:60
+        hidden = tuple(int(h) for h in hidden)
+        if kind == KIND_SIMPLE:
+            if not 1 <= len(hidden) <= 6:
+                raise NativeError("SimpleWavefunction: 1..6 hidden layers")
+            net = _Net(kind, hidden[0], hidden[1] if len(hidden) > 1 else 0, 0, 0, 0,
+                       float(envelope_decay), float(cusp_same), float(cusp_diff), len(hidden), ACTIVATIONS[activation],
+                       (C.c_int32 * 6)(*hidden))
+        else:
+            net = _Net(kind, hidden[0], hidden[1], int(bool(use_cusp)), int(bool(use_backflow)), 0,
+                       float(envelope_decay), float(cusp_same), float(cusp_diff), 0, 0, (C.c_int32 * 6)())
         h = C.c_void_p()
         rc = self.lib.nqmc_create(C.byref(sysm), C.byref(net), self.device, C.byref(h))
         if rc != 0:
@@ -136,7 +338,6 @@ class Context:
         self.h = h
         self.P = int(self.lib.nqmc_param_count(self.h))
         self.cap = 0
-        self._theta_version = None
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -151,12 +352,22 @@ class Context:
         if rc != 0:
             raise NativeError(f"{what} failed ({rc}): {self.lib.nqmc_last_error(self.h).decode()}")
 
-    @property
-    def stream(self) -> int:
-        return _torch().cuda.current_stream(self.device).cuda_stream
-
     def dev(self):
-        return _torch().device("cuda", self.device)
+        """torch.device of this context -- a convenience for callers that use torch (the tests); imports torch."""
+        import torch
+        return torch.device("cuda", self.device)
+
+    def empty(self, shape, dtype=np.float32) -> DeviceArray:
+        return DeviceArray(shape, dtype, self.device)
+
+    def zeros(self, shape, dtype=np.float32) -> DeviceArray:
+        return DeviceArray(shape, dtype, self.device).zero_(self.stream)
+
+    def upload(self, a, dtype=np.float32):
+        return to_device(a, dtype, self.device, self.stream)
+
+    def synchronize(self):
+        _mem_check(self.lib.nqmc_stream_sync(self.device, self.stream), "nqmc_stream_sync")
 
     def reserve(self, W: int):
         if W > self.cap:
@@ -178,18 +389,16 @@ class Context:
 
     # ------------------------------------------------------------------ parameters
     def set_params(self, theta):
-        """theta: numpy float32 (P,) on host, or a torch CUDA float32 tensor."""
-        torch = _torch()
-        if isinstance(theta, np.ndarray):
+        """theta: numpy float32 (P,) on host, or a device buffer (data_ptr()) of P floats."""
+        if hasattr(theta, "data_ptr"):
+            if int(np.prod(_shape(theta))) != self.P:
+                raise ValueError(f"theta must have shape ({self.P},)")
+            self._check(self.lib.nqmc_set_params(self.h, _ptr(theta), self.P, self.stream), "nqmc_set_params")
+        else:
             th = np.ascontiguousarray(theta, dtype=np.float32)
             if th.shape != (self.P,):
                 raise ValueError(f"theta must have shape ({self.P},), got {th.shape}")
             self._check(self.lib.nqmc_set_params_host(self.h, th.ctypes.data, self.P, self.stream), "nqmc_set_params_host")
-        else:
-            th = theta.to(self.dev(), torch.float32).contiguous()
-            if tuple(th.shape) != (self.P,):
-                raise ValueError(f"theta must have shape ({self.P},)")
-            self._check(self.lib.nqmc_set_params(self.h, th.data_ptr(), self.P, self.stream), "nqmc_set_params")
 
     def get_params(self) -> np.ndarray:
         th = np.empty(self.P, dtype=np.float32)
@@ -199,93 +408,101 @@ class Context:
     def adam_step(self, gsum, hdr, m, v, count: int, lr: float, clip: float, grad_norm=None):
         """Fused clip + Adam on the device; theta inside the ctx is updated in place."""
         self.reserve(max(self.cap, 1))
-        self._check(self.lib.nqmc_adam_step(self.h, gsum.data_ptr(), hdr.data_ptr(), m.data_ptr(), v.data_ptr(), int(count),
+        self._check(self.lib.nqmc_adam_step(self.h, _ptr(gsum), _ptr(hdr), _ptr(m), _ptr(v), int(count),
                                             float(lr), float(clip), _ptr(grad_norm), self.stream), "nqmc_adam_step")
 
     # ------------------------------------------------------------------ layout
-    def to_soa(self, r_aos):
-        """(W,N,3) numpy / torch -> device SoA tensor [3N, W]."""
-        torch = _torch()
-        a = torch.as_tensor(np.ascontiguousarray(r_aos, dtype=np.float32) if isinstance(r_aos, np.ndarray) else r_aos)
-        a = a.to(self.dev(), torch.float32).contiguous()
-        W = a.shape[0]
-        if tuple(a.shape[1:]) != (self.n_elec, 3):
-            raise ValueError(f"positions must have shape (W,{self.n_elec},3), got {tuple(a.shape)}")
+    def to_soa(self, r_aos) -> DeviceArray:
+        """(W,N,3) numpy / device buffer -> device SoA [3N, W]."""
+        a = self.upload(r_aos)
+        shp = _shape(a)
+        W = shp[0]
+        if tuple(shp[1:]) != (self.n_elec, 3):
+            raise ValueError(f"positions must have shape (W,{self.n_elec},3), got {tuple(shp)}")
         self.reserve(W)
-        soa = torch.empty((3 * self.n_elec, W), dtype=torch.float32, device=self.dev())
-        self._check(self.lib.nqmc_aos_to_soa(self.h, a.data_ptr(), soa.data_ptr(), W, self.stream), "nqmc_aos_to_soa")
+        soa = self.empty((3 * self.n_elec, W))
+        self._check(self.lib.nqmc_aos_to_soa(self.h, _ptr(a), soa.ptr, W, self.stream), "nqmc_aos_to_soa")
+        if not isinstance(r_aos, DeviceArray) and not hasattr(r_aos, "data_ptr"):
+            self.synchronize()          # `a` is a temporary upload; keep it alive until the transpose has run
         return soa
 
-    def to_aos(self, soa):
-        torch = _torch()
-        W = soa.shape[1]
-        a = torch.empty((W, self.n_elec, 3), dtype=torch.float32, device=self.dev())
-        self._check(self.lib.nqmc_soa_to_aos(self.h, soa.data_ptr(), a.data_ptr(), W, self.stream), "nqmc_soa_to_aos")
+    def to_aos(self, soa) -> DeviceArray:
+        W = _shape(soa)[1]
+        a = self.empty((W, self.n_elec, 3))
+        self._check(self.lib.nqmc_soa_to_aos(self.h, _ptr(soa), a.ptr, W, self.stream), "nqmc_soa_to_aos")
         return a
 
-    # ------------------------------------------------------------------ hot path (device tensors, SoA)
+    # ------------------------------------------------------------------ hot path (device buffers, SoA)
     def log_psi(self, r_soa):
-        torch = _torch()
-        W = r_soa.shape[1]
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        la = torch.empty(W, dtype=torch.float32, device=self.dev())
-        sg = torch.empty(W, dtype=torch.float32, device=self.dev())
-        self._check(self.lib.nqmc_log_psi(self.h, r_soa.data_ptr(), W, la.data_ptr(), sg.data_ptr(), self.stream), "nqmc_log_psi")
+        la, sg = self.empty(W), self.empty(W)
+        self._check(self.lib.nqmc_log_psi(self.h, _ptr(r_soa), W, la.ptr, sg.ptr, self.stream), "nqmc_log_psi")
         return sg, la
 
     def mh_step(self, r_soa, logp, sigma: float, normals=None, uniforms=None, seed: int = 0, step: int = 0,
                 walker_id0: int = 0, accept=None, n_accepted=None):
-        W = r_soa.shape[1]
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        self._check(self.lib.nqmc_mh_step(self.h, r_soa.data_ptr(), logp.data_ptr(), _ptr(normals), _ptr(uniforms),
+        self._check(self.lib.nqmc_mh_step(self.h, _ptr(r_soa), _ptr(logp), _ptr(normals), _ptr(uniforms),
                                           int(seed) & (2**64 - 1), int(step), int(walker_id0), float(sigma), W,
                                           _ptr(accept), _ptr(n_accepted), self.stream), "nqmc_mh_step")
 
-    def local_energy(self, r_soa, want_parts: bool = False):
-        torch = _torch()
-        W = r_soa.shape[1]
+    def sample(self, r_soa, logp, sigma: float, n_burn: int, n_samples: int, n_thin: int, samples, n_accepted=None,
+               seed_burn: int = 0, seed_sample: int = 0, walker_id0: int = 0, normals=None, uniforms=None,
+               sigma_dev=None, target_acceptance: float = 0.5, adapt_every: int = 0):
+        """MetropolisSampler.sample on the device (nqmc_sample): walkers stay resident, kept samples land in
+        ``samples`` [3N][n_samples][W]."""
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        e = torch.empty(W, dtype=torch.float32, device=self.dev())
-        parts = torch.empty((4, W), dtype=torch.float32, device=self.dev()) if want_parts else None
-        self._check(self.lib.nqmc_local_energy(self.h, r_soa.data_ptr(), W, e.data_ptr(), _ptr(parts), self.stream), "nqmc_local_energy")
+        self._check(self.lib.nqmc_sample(self.h, _ptr(r_soa), _ptr(logp), _ptr(normals), _ptr(uniforms),
+                                         int(seed_burn) & (2**64 - 1), int(seed_sample) & (2**64 - 1), int(walker_id0),
+                                         float(sigma), W, int(n_burn), int(n_samples), int(n_thin), _ptr(samples),
+                                         _ptr(n_accepted), _ptr(sigma_dev), float(target_acceptance), int(adapt_every),
+                                         self.stream), "nqmc_sample")
+
+    def local_energy(self, r_soa, want_parts: bool = False):
+        W = _shape(r_soa)[1]
+        self.reserve(W)
+        e = self.empty(W)
+        parts = self.empty((4, W)) if want_parts else None
+        self._check(self.lib.nqmc_local_energy(self.h, _ptr(r_soa), W, e.ptr, _ptr(parts), self.stream), "nqmc_local_energy")
         return (e, parts) if want_parts else e
 
     def grad_accum(self, r_soa, weight=None):
-        torch = _torch()
-        W = r_soa.shape[1]
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        out = torch.empty(self.P, dtype=torch.float64, device=self.dev())
-        self._check(self.lib.nqmc_grad_accum(self.h, r_soa.data_ptr(), _ptr(weight), W, out.data_ptr(), self.stream), "nqmc_grad_accum")
+        out = self.empty(self.P, np.float64)
+        self._check(self.lib.nqmc_grad_accum(self.h, _ptr(r_soa), _ptr(weight), W, out.ptr, self.stream), "nqmc_grad_accum")
         return out
 
     def energy_stats(self, e_l):
-        torch = _torch()
-        W = e_l.shape[0]
+        W = _shape(e_l)[0]
         self.reserve(W)
-        hdr = torch.empty(HDR_SIZE, dtype=torch.float64, device=self.dev())
-        self._check(self.lib.nqmc_energy_stats(self.h, e_l.data_ptr(), W, hdr.data_ptr(), self.stream), "nqmc_energy_stats")
+        hdr = self.empty(HDR_SIZE, np.float64)
+        self._check(self.lib.nqmc_energy_stats(self.h, _ptr(e_l), W, hdr.ptr, self.stream), "nqmc_energy_stats")
         return hdr
 
     def walker_step_a(self, r_soa, logp, sigma, e_l, hdr, normals=None, uniforms=None, seed=0, step=0, walker_id0=0,
                       n_accepted=None):
-        W = r_soa.shape[1]
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        self._check(self.lib.nqmc_walker_step_a(self.h, r_soa.data_ptr(), logp.data_ptr(), _ptr(normals), _ptr(uniforms),
+        self._check(self.lib.nqmc_walker_step_a(self.h, _ptr(r_soa), _ptr(logp), _ptr(normals), _ptr(uniforms),
                                                 int(seed) & (2**64 - 1), int(step), int(walker_id0), float(sigma), W,
-                                                e_l.data_ptr(), _ptr(n_accepted), hdr.data_ptr(), self.stream), "nqmc_walker_step_a")
+                                                _ptr(e_l), _ptr(n_accepted), _ptr(hdr), self.stream), "nqmc_walker_step_a")
 
     def walker_step_b(self, r_soa, e_l, hdr, gsum):
-        W = r_soa.shape[1]
-        self._check(self.lib.nqmc_walker_step_b(self.h, r_soa.data_ptr(), e_l.data_ptr(), W, hdr.data_ptr(), gsum.data_ptr(),
+        W = _shape(r_soa)[1]
+        self._check(self.lib.nqmc_walker_step_b(self.h, _ptr(r_soa), _ptr(e_l), W, _ptr(hdr), _ptr(gsum),
                                                 self.stream), "nqmc_walker_step_b")
 
     def walker_step(self, r_soa, logp, sigma, e_l, hdr, gsum, normals=None, uniforms=None, seed=0, step=0,
                     walker_id0=0, n_accepted=None):
-        W = r_soa.shape[1]
+        W = _shape(r_soa)[1]
         self.reserve(W)
-        self._check(self.lib.nqmc_walker_step(self.h, r_soa.data_ptr(), logp.data_ptr(), _ptr(normals), _ptr(uniforms),
+        self._check(self.lib.nqmc_walker_step(self.h, _ptr(r_soa), _ptr(logp), _ptr(normals), _ptr(uniforms),
                                               int(seed) & (2**64 - 1), int(step), int(walker_id0), float(sigma), W,
-                                              e_l.data_ptr(), _ptr(n_accepted), hdr.data_ptr(), gsum.data_ptr(),
+                                              _ptr(e_l), _ptr(n_accepted), _ptr(hdr), _ptr(gsum),
                                               self.stream), "nqmc_walker_step")
 
     def walker_step_host(self, r_aos: np.ndarray, logp: np.ndarray, sigma: float, e_l: np.ndarray, hdr: np.ndarray,
@@ -316,8 +533,12 @@ class Context:
         self._check(self.lib.nqmc_comm_attach(self.h, C.cast(buf, C.c_void_p)), "nqmc_comm_attach")
 
     def comm_allreduce(self, vec) -> None:
-        """In-place sum over ranks of a float64 device tensor (len <= max(param_count, 8))."""
-        self._check(self.lib.nqmc_comm_allreduce(self.h, vec.data_ptr(), vec.numel(), self.stream), "nqmc_comm_allreduce")
+        """In-place sum over ranks of a float64 device buffer (len <= max(param_count, 8))."""
+        self._check(self.lib.nqmc_comm_allreduce(self.h, _ptr(vec), int(np.prod(_shape(vec))), self.stream),
+                    "nqmc_comm_allreduce")
+
+    def comm_active(self) -> bool:
+        return bool(self.lib.nqmc_comm_active(self.h))
 
     def use_tensor_cores(self, enable: bool):
         self._check(self.lib.nqmc_use_tensor_cores(self.h, int(enable)), "nqmc_use_tensor_cores")
@@ -337,9 +558,7 @@ class Context:
         return tf.value
 
     def rng_fill(self, W: int, seed: int, step: int, walker_id0: int = 0):
-        torch = _torch()
-        n = torch.empty((3 * self.n_elec, W), dtype=torch.float32, device=self.dev())
-        u = torch.empty(W, dtype=torch.float32, device=self.dev())
-        self._check(self.lib.nqmc_rng_fill(self.h, int(seed) & (2**64 - 1), int(step), int(walker_id0), W, n.data_ptr(),
-                                           u.data_ptr(), self.stream), "nqmc_rng_fill")
+        n, u = self.empty((3 * self.n_elec, W)), self.empty(W)
+        self._check(self.lib.nqmc_rng_fill(self.h, int(seed) & (2**64 - 1), int(step), int(walker_id0), W, n.ptr,
+                                           u.ptr, self.stream), "nqmc_rng_fill")
         return n, u

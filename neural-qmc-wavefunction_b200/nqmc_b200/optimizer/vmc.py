@@ -6,14 +6,23 @@ dataclass fields, metric keys (energy, energy_std, acceptance_rate, grad_norm) a
 signature.  Differences, all on purpose:
   * sampling, E_L and the gradient estimator run as CUDA kernels over the whole batch; the
     per-sample gradient matrix (n_total x P, vmc.py:123) is never materialised;
+  * walkers, log-probabilities and samples stay on the GPU from one iteration to the next (the arrays in
+    ``state.sampler_state`` are device buffers that convert to NumPy on demand); per iteration the host sees the
+    8-double statistics header, the gradient (host update) or its norm (``device_update=True``), nothing else;
   * the gradient is centred with the batch mean exactly as vmc.py:113-133, via two device phases
     (energies -> mean -> weighted reverse pass) so that multi-GPU runs need only two tiny all-reduces;
+    with ``n_samples == 1`` the sampled move, E_L and the reverse pass are the library's fused walker step
+    (``nqmc_walker_step``, the call bench.py times);
   * the Adam + global-norm-clip update (optax.chain(clip_by_global_norm, adam), vmc.py:180-184,
-    256-261) is restated in NumPy on the host -- the reference runs it on the host too.
+    256-261) is restated in NumPy on the host -- the reference runs it on the host too -- or runs fused on
+    the device (``device_update=True``, nqmc_adam_step).
 Quirk kept: ``sampler_state.log_prob`` is carried across the parameter update.
+Extra metric keys (beyond the reference's four): ``n_bad`` -- walkers whose E_L was not finite and which the
+device reductions excluded (the reference would propagate NaN); a warning is issued above 1 %.
 """
 from __future__ import annotations
 
+import warnings
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, NamedTuple, Optional, Tuple
 
@@ -21,9 +30,9 @@ import numpy as np
 
 from .. import parallel
 from .. import random as nqrandom
-from .._native import HDR_N, HDR_N_BAD, HDR_SUM_E, HDR_SUM_E2
+from .._native import HDR_N, HDR_N_ACCEPT, HDR_N_BAD, HDR_SUM_E, HDR_SUM_E2, DeviceArray
 from ..params import Params, ravel, tree_leaves, unravel
-from ..sampler.metropolis import MetropolisSampler, SamplerState
+from ..sampler.metropolis import MetropolisSampler, SamplerState, WalkerArray, _resident, _streams_to_device
 
 
 class VMCState(NamedTuple):
@@ -33,39 +42,51 @@ class VMCState(NamedTuple):
     step: int
 
 
+def _samples_to_device(ctx, samples):
+    if hasattr(samples, "data_ptr"):
+        return samples
+    flat = np.asarray(samples, dtype=np.float32)
+    return ctx.to_soa(flat.reshape(-1, *flat.shape[-2:]))                      # vmc.py:105
+
+
 def _energies_device(wavefunction, params, samples, molecule):
-    """-> (ctx, r_soa, e_l, hdr) for samples (n_samples,n_chains,N,3) host array or a device SoA tensor."""
+    """-> (ctx, r_soa, e_l, hdr) for samples (n_samples,n_chains,N,3) host array or a device SoA buffer."""
     ctx = wavefunction.context(molecule)
     ctx.set_params(ravel(params))
-    if isinstance(samples, np.ndarray):
-        flat = np.asarray(samples, dtype=np.float32).reshape(-1, *samples.shape[-2:])     # vmc.py:105
-        r = ctx.to_soa(flat)
-    else:
-        r = samples
+    r = _samples_to_device(ctx, samples)
     e = ctx.local_energy(r)
     hdr = ctx.energy_stats(e)
-    parallel.all_reduce_sum_(hdr)
+    parallel.reduce_over_ranks_(ctx, hdr)
     return ctx, r, e, hdr
+
+
+def _stats(h) -> Tuple[float, float, float]:
+    n = float(h[HDR_N])
+    if n <= 0:
+        raise FloatingPointError("no walker with a finite local energy in this batch (hdr[N] == 0)")
+    mean = float(h[HDR_SUM_E]) / n
+    var = max(float(h[HDR_SUM_E2]) / n - mean * mean, 0.0)
+    bad = float(h[HDR_N_BAD])
+    if bad > 0.01 * (n + bad):
+        warnings.warn(f"{int(bad)} of {int(n + bad)} walkers had a non-finite local energy and were excluded "
+                      "from the mean and the gradient (the reference would return NaN)", RuntimeWarning)
+    return mean, np.sqrt(var) / np.sqrt(n), bad
 
 
 def estimate_energy(wavefunction, params, samples, molecule) -> Tuple[float, float]:
     """(mean_energy, energy_std) (vmc.py:49-79); energy_std = std(ddof=0)/sqrt(n)."""
-    _, _, _, hdr = _energies_device(wavefunction, params, samples, molecule)
-    h = hdr.cpu().numpy()
-    n = h[HDR_N]
-    mean = h[HDR_SUM_E] / n
-    var = max(h[HDR_SUM_E2] / n - mean * mean, 0.0)
-    return np.float32(mean), np.float32(np.sqrt(var) / np.sqrt(n))
+    ctx, _, _, hdr = _energies_device(wavefunction, params, samples, molecule)
+    mean, std, _ = _stats(hdr.numpy(ctx.stream))
+    return np.float32(mean), np.float32(std)
 
 
 def compute_gradient(wavefunction, params, samples, molecule) -> Tuple[Params, float, float]:
     """(gradient pytree, mean_energy, energy_std) (vmc.py:82-135): 2 <(E_L - <E_L>) d log|psi| / d theta>."""
-    import torch
     ctx, r, e, hdr = _energies_device(wavefunction, params, samples, molecule)
-    gsum = torch.empty(ctx.P, dtype=torch.float64, device=ctx.dev())
+    gsum = ctx.empty(ctx.P, np.float64)
     ctx.walker_step_b(r, e, hdr, gsum)
-    parallel.all_reduce_sum_(gsum)
-    grad, mean, std = parallel.combine_gradient(hdr.cpu().numpy(), gsum.cpu().numpy())
+    parallel.reduce_over_ranks_(ctx, gsum)
+    grad, mean, std = parallel.combine_gradient(hdr.numpy(ctx.stream), gsum.numpy(ctx.stream))
     return unravel(grad.astype(np.float32), params), np.float32(mean), np.float32(std)
 
 
@@ -82,9 +103,9 @@ def _opt_update(grad_flat: np.ndarray, opt_state, lr: float, clip: float):
     if norm >= clip:                                    # optax: keep g when ||g|| < max_norm
         g = (g / np.float32(norm)) * np.float32(clip)
     b1, b2, eps = 0.9, 0.999, 1e-8
-    count = opt_state["count"] + 1
-    mu = b1 * opt_state["mu"] + (1 - b1) * g
-    nu = b2 * opt_state["nu"] + (1 - b2) * g * g
+    count = int(opt_state["count"]) + 1
+    mu = b1 * np.asarray(opt_state["mu"], dtype=np.float32) + (1 - b1) * g      # moments may live on the device
+    nu = b2 * np.asarray(opt_state["nu"], dtype=np.float32) + (1 - b2) * g * g
     mhat = mu / (1 - b1 ** count)
     vhat = nu / (1 - b2 ** count)
     upd = (-lr * mhat / (np.sqrt(vhat) + eps)).astype(np.float32)
@@ -100,83 +121,105 @@ class VMCOptimizer:
     step_size: float = 0.5
     clip_grad: float = 1.0
     device_update: bool = False     # extension: fused clip + Adam on the GPU, theta stays resident
+    adaptive_step: bool = False     # extension: adapt step_size toward target_acceptance in burn-in
+    target_acceptance: float = 0.5
 
     def _local_chains(self) -> Tuple[int, int]:
         rank, ws = parallel.world()
         return parallel.shard_range(self.n_chains, rank, ws)
 
+    def _sampler(self) -> MetropolisSampler:
+        s = getattr(self, "_sampler_obj", None)
+        if s is None or not self.adaptive_step:
+            s = MetropolisSampler(step_size=self.step_size, target_acceptance=self.target_acceptance,
+                                  adaptive=self.adaptive_step)                 # vmc.py:241 builds one per step
+            self._sampler_obj = s
+        return s
+
     def init(self, key, wavefunction, params: Params, molecule) -> VMCState:
         opt_state = _opt_init(params)                                         # vmc.py:180-184
-        sampler = MetropolisSampler(step_size=self.step_size)
         R = np.asarray(molecule.positions, dtype=np.float32)
         n_el = molecule.n_electrons
         init_positions = np.stack([R[i % molecule.n_atoms] for i in range(n_el)], axis=0)    # vmc.py:199-203
         lo, hi = self._local_chains()
         # draw for all global chains, keep this rank's block: positions do not depend on the rank count
         noise = nqrandom.normal(key, (self.n_chains, n_el, 3))[lo:hi]
-        positions = init_positions[None] + np.float32(0.5) * noise            # init_width=0.5 (vmc.py:206)
-        wavefunction.context(molecule)                                        # bind geometry before first call
-        log_prob = np.asarray(wavefunction.log_prob(params, positions), dtype=np.float32)
-        st = SamplerState(positions.astype(np.float32), log_prob, np.zeros(hi - lo, dtype=np.float32), 0)
+        positions = (init_positions[None] + np.float32(0.5) * noise).astype(np.float32)   # init_width=0.5 (vmc.py:206)
+        ctx = wavefunction.context(molecule)       # one context (geometry + charges) for sampling and energies
+        ctx.set_params(ravel(params))
+        r = ctx.to_soa(positions)
+        _, la = ctx.log_psi(r)
+        logp = ctx.upload((2.0 * la.numpy(ctx.stream)).astype(np.float32))    # base.py:76
+        st = SamplerState(WalkerArray(ctx, r), logp, ctx.zeros(hi - lo), 0)
         return VMCState(params=params, opt_state=opt_state, sampler_state=st, step=0)
 
-    def step(self, key, state: VMCState, wavefunction, molecule) -> Tuple[VMCState, Dict[str, float]]:
-        import torch
+    def step(self, key, state: VMCState, wavefunction, molecule, *, normals=None, uniforms=None
+             ) -> Tuple[VMCState, Dict[str, float]]:
+        """One VMC iteration (vmc.py:217-282).  ``normals`` (n_burn_eff + n_samples, n_chains, N, 3) / ``uniforms``
+        (n_burn_eff + n_samples, n_chains) replace the device RNG streams (parity mode)."""
         params = state.params
+        ctx = wavefunction.context(molecule)
+        ctx.set_params(ravel(params))
         log_prob_fn = wavefunction.log_prob_fn(params)                        # vmc.py:238-239
-        sampler = MetropolisSampler(step_size=self.step_size)
+        sampler = self._sampler()
         lo, hi = self._local_chains()
-        samples, sampler_state, acc = sampler.sample_device(
-            key, log_prob_fn, state.sampler_state, n_samples=self.n_samples,
-            n_burn=self.n_burn if state.step == 0 else 10, n_thin=1, walker_id0=lo)[:3]       # vmc.py:242-248
-        rank, ws = parallel.world()
+        n_burn = self.n_burn if state.step == 0 else 10                      # vmc.py:247
+        W = hi - lo
+        if self.n_samples == 1 and normals is None and uniforms is None:
+            # burn-in, then the library's fused walker step: sampled move + E_L + header + centred reverse pass
+            _, sstate, _, _ = sampler.sample_device(key, log_prob_fn, state.sampler_state, 0, n_burn, 1, walker_id0=lo,
+                                                    donate=True, want_rate=False)
+            r, logp = sstate.positions.soa, sstate.log_prob
+            e, hdr, gsum = ctx.empty(W), ctx.empty(8, np.float64), ctx.empty(ctx.P, np.float64)
+            nacc = ctx.zeros(W)
+            k_samp = nqrandom.split(key, 2)[1]
+            seed = nqrandom.key_to_seed(k_samp)
+            if ctx.comm_active() or parallel.world()[1] == 1:                 # both sums run in-stream (or are not needed)
+                ctx.walker_step(r, logp, sampler.step_size, e, hdr, gsum, seed=seed, step=0, walker_id0=lo, n_accepted=nacc)
+            else:                                                             # process-group sums between the two phases
+                ctx.walker_step_a(r, logp, sampler.step_size, e, hdr, seed=seed, step=0, walker_id0=lo, n_accepted=nacc)
+                parallel.all_reduce_sum_(hdr)
+                ctx.walker_step_b(r, e, hdr, gsum)
+                parallel.all_reduce_sum_(gsum)
+            sampler_state = SamplerState(WalkerArray(ctx, r), logp, nacc, 1)
+            h = hdr.numpy(ctx.stream)
+            acc = float(h[HDR_N_ACCEPT]) / max(float(h[HDR_N]) + float(h[HDR_N_BAD]), 1.0)
+        else:
+            samples, sampler_state, acc, _ = sampler.sample_device(
+                key, log_prob_fn, state.sampler_state, n_samples=self.n_samples, n_burn=n_burn, n_thin=1,
+                walker_id0=lo, donate=True, normals=normals, uniforms=uniforms)                   # vmc.py:242-248
+            e = ctx.local_energy(samples)                                     # vmc.py:109-111
+            hdr = ctx.energy_stats(e)
+            parallel.reduce_over_ranks_(ctx, hdr)
+            gsum = ctx.empty(ctx.P, np.float64)
+            ctx.walker_step_b(samples, e, hdr, gsum)                          # vmc.py:117-133
+            parallel.reduce_over_ranks_(ctx, gsum)
+            h = hdr.numpy(ctx.stream)
+            rank, ws = parallel.world()
+            if ws > 1:
+                a = parallel.group().all_reduce_sum(np.array([acc * W, float(W)]))
+                acc = float(a[0] / a[1])
+        mean, std, n_bad = _stats(h)
         if self.device_update:
-            new_state, metrics = self._device_update(state, wavefunction, molecule, samples, sampler_state, acc, lo, hi)
-            return new_state, metrics
-        gradient, mean_energy, energy_std = compute_gradient(wavefunction, params, samples, molecule)
-        if ws > 1:
-            a = torch.tensor([acc * (hi - lo), float(hi - lo)], dtype=torch.float64,
-                             device=samples.device if torch.distributed.get_backend() == "nccl" else "cpu")
-            parallel.all_reduce_sum_(a)
-            acc = float(a[0] / a[1])
-        g = ravel(gradient)
-        upd, opt_state = _opt_update(g, state.opt_state, self.learning_rate, self.clip_grad)  # vmc.py:256-259
-        new_params = unravel(ravel(params) + upd, params)                     # optax.apply_updates
-        grad_norm = float(np.sqrt(sum(float(np.sum(np.asarray(l, dtype=np.float64) ** 2)) for l in tree_leaves(gradient))))
+            opt = state.opt_state
+            mu = opt["mu"] if isinstance(opt["mu"], DeviceArray) else ctx.upload(np.asarray(opt["mu"], np.float32))
+            nu = opt["nu"] if isinstance(opt["nu"], DeviceArray) else ctx.upload(np.asarray(opt["nu"], np.float32))
+            gn = ctx.zeros(1, np.float64)
+            count = int(opt["count"]) + 1
+            ctx.adam_step(gsum, hdr, mu, nu, count, self.learning_rate, self.clip_grad, grad_norm=gn)   # vmc.py:256-266
+            new_params = unravel(ctx.get_params(), params)
+            opt_state = {"count": count, "mu": mu, "nu": nu}
+            grad_norm = float(gn.numpy(ctx.stream)[0])
+        else:
+            g = (2.0 * gsum.numpy(ctx.stream) / float(h[HDR_N])).astype(np.float32)               # vmc.py:126-133
+            upd, opt_state = _opt_update(g, state.opt_state, self.learning_rate, self.clip_grad)  # vmc.py:256-259
+            new_params = unravel(ravel(params) + upd, params)                 # optax.apply_updates
+            grad_norm = float(np.sqrt(np.sum(g.astype(np.float64) ** 2)))    # vmc.py:264-266
         new_state = VMCState(new_params, opt_state, sampler_state, state.step + 1)
-        metrics = {"energy": float(mean_energy), "energy_std": float(energy_std), "acceptance_rate": float(acc),
-                   "grad_norm": grad_norm}
-        return new_state, metrics
-
-    def _device_update(self, state, wavefunction, molecule, samples, sampler_state, acc, lo, hi):
-        """E_L, centred gradient sums, global-norm clip and Adam all on the device (nqmc_adam_step)."""
-        import torch
-        params = state.params
-        ctx, r, e, hdr = _energies_device(wavefunction, params, samples, molecule)
-        dev = ctx.dev()
-        gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
-        ctx.walker_step_b(r, e, hdr, gsum)
-        parallel.all_reduce_sum_(gsum)
-        opt = state.opt_state
-        mu = torch.as_tensor(opt["mu"]).to(dev, torch.float32).contiguous()
-        nu = torch.as_tensor(opt["nu"]).to(dev, torch.float32).contiguous()
-        gn = torch.zeros(1, dtype=torch.float64, device=dev)
-        count = int(opt["count"]) + 1
-        ctx.adam_step(gsum, hdr, mu, nu, count, self.learning_rate, self.clip_grad, grad_norm=gn)
-        new_params = unravel(ctx.get_params(), params)
-        h = hdr.cpu().numpy()
-        n = h[HDR_N]
-        mean = h[HDR_SUM_E] / n
-        var = max(h[HDR_SUM_E2] / n - mean * mean, 0.0)
-        rank, ws = parallel.world()
-        if ws > 1:
-            a = torch.tensor([acc * (hi - lo), float(hi - lo)], dtype=torch.float64,
-                             device=dev if torch.distributed.get_backend() == "nccl" else "cpu")
-            parallel.all_reduce_sum_(a)
-            acc = float(a[0] / a[1])
-        new_state = VMCState(new_params, {"count": count, "mu": mu, "nu": nu}, sampler_state, state.step + 1)
-        metrics = {"energy": float(mean), "energy_std": float(np.sqrt(var) / np.sqrt(n)), "acceptance_rate": float(acc),
-                   "grad_norm": float(gn.item())}
+        metrics = {"energy": float(mean), "energy_std": float(std), "acceptance_rate": float(acc),
+                   "grad_norm": grad_norm, "n_bad": float(n_bad)}
+        if self.adaptive_step:
+            metrics["step_size"] = float(sampler.step_size)
         return new_state, metrics
 
     def train(self, key, wavefunction, params: Params, molecule, n_steps: int, log_every: int = 10,

@@ -5,12 +5,12 @@ The reference trains one geometry after another in a Python loop.  Geometries sh
 its own nuclei, V_nn, parameters theta and walkers -- so they are independent units: no collective, and
 across GPUs geometry g simply runs on rank g % world.  Here every geometry owns a device context; one
 `step()` advances all local geometries by one fused walker step (MH move, E_L, weighted gradient sums),
-back to back on the current stream (each launch already fills the 148 SMs at >= 16k walkers).
+back to back on one stream (each launch already fills the 148 SMs at >= 16k walkers).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from dataclasses import dataclass
+from typing import List, Sequence
 
 import numpy as np
 
@@ -39,7 +39,6 @@ class GeometrySweep:
     def __init__(self, bond_lengths: Sequence[float] = tuple(np.linspace(1.0, 4.0, 16)), n_atoms: int = 4,
                  walkers_per_geometry: int = 16384, hidden=(64, 64), use_cusp: bool = False, use_backflow: bool = False,
                  step_size: float = 0.5, seed: int = 42):
-        import torch
         self.step_size, self.seed, self.W = float(step_size), int(seed), int(walkers_per_geometry)
         rank, ws = parallel.world()
         self.local_ids = [g for g in range(len(bond_lengths)) if g % ws == rank]
@@ -57,11 +56,9 @@ class GeometrySweep:
             r0 = (pos + 0.5 * rng.standard_normal((self.W, mol.n_electrons, 3))).astype(np.float32)
             r = ctx.to_soa(r0)
             _, la = ctx.log_psi(r)
-            dev = ctx.dev()
-            self.states.append(GeometryState(R, mol, wf, params, ctx, r, (2.0 * la).contiguous(),
-                                             torch.empty(self.W, dtype=torch.float32, device=dev),
-                                             torch.empty(8, dtype=torch.float64, device=dev),
-                                             torch.empty(ctx.P, dtype=torch.float64, device=dev)))
+            logp = ctx.upload((2.0 * la.numpy(ctx.stream)).astype(np.float32))
+            self.states.append(GeometryState(R, mol, wf, params, ctx, r, logp, ctx.empty(self.W),
+                                             ctx.empty(8, np.float64), ctx.empty(ctx.P, np.float64)))
         self.t = 0
 
     def burn_in(self, n_steps: int):
@@ -70,16 +67,20 @@ class GeometrySweep:
                 st.ctx.mh_step(st.r, st.logp, self.step_size, seed=self.seed + 1000 * g, step=t)
 
     def step(self):
-        """One fused walker step for every local geometry; returns [(bond, mean E, stderr, grad)] lazily as device data."""
+        """One fused walker step for every local geometry; results stay on the device until ``results()``."""
         self.t += 1
         for st, g in zip(self.states, self.local_ids):
             st.ctx.walker_step(st.r, st.logp, self.step_size, st.e_l, st.hdr, st.gsum, seed=self.seed + 1000 * g,
                                step=(1 << 20) + self.t)
 
+    def synchronize(self):
+        for st in self.states:
+            st.ctx.synchronize()
+
     def results(self):
         out = []
         for st in self.states:
-            grad, mean, std = parallel.combine_gradient(st.hdr.cpu().numpy(), st.gsum.cpu().numpy())
+            grad, mean, std = parallel.combine_gradient(st.hdr.numpy(st.ctx.stream), st.gsum.numpy(st.ctx.stream))
             out.append({"bond_length": st.bond_length, "energy": mean, "std": std, "gradient": grad,
                         "v_nn": st.molecule.nuclear_repulsion_energy()})
         return out

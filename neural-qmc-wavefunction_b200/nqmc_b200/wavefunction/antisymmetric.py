@@ -48,6 +48,7 @@ class AntisymmetricWavefunction(Wavefunction):
         if nuclear_positions is None:
             raise ValueError("AntisymmetricWavefunction needs the geometry: pass molecule= or nuclear_positions=")
         self.nuclear_positions = np.asarray(nuclear_positions, dtype=np.float64).reshape(-1, 3)
+        self._charges_given = charges is not None
         self.charges = (np.ones(len(self.nuclear_positions)) if charges is None
                         else np.asarray(charges, dtype=np.float64).reshape(-1))
 
@@ -56,7 +57,15 @@ class AntisymmetricWavefunction(Wavefunction):
             R = np.asarray(molecule.positions, dtype=np.float64)
             if R.shape != self.nuclear_positions.shape or not np.allclose(R, self.nuclear_positions):
                 raise ValueError("molecule geometry differs from the wavefunction's nuclear_positions")
-            return R, np.asarray(molecule.charges, dtype=np.float64), self.n_up, self.n_down, float(molecule.nuclear_repulsion_energy())
+            Z = np.asarray(molecule.charges, dtype=np.float64).reshape(-1)
+            if self._charges_given and not np.allclose(Z, self.charges):
+                raise ValueError("molecule charges differ from the wavefunction's charges")
+            # bind: from now on the sampler (which calls context() without a molecule) and the energy pass
+            # (which passes one) resolve to the SAME native context -- same charges, same V_nn
+            self.charges, self._charges_given = Z, True
+            self._v_nn = float(molecule.nuclear_repulsion_energy())
+            if tuple(molecule.spin) != (self.n_up, self.n_down):
+                raise ValueError(f"molecule spin {molecule.spin} differs from (n_up, n_down)=({self.n_up},{self.n_down})")
         return self.nuclear_positions, self.charges, self.n_up, self.n_down, self._v_nn
 
     def _net_args(self):

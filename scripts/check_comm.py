@@ -14,6 +14,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "neural-qmc-wav
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 from nqmc_b200 import parallel  # noqa: E402
 import bench  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+from _util import T  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -84,7 +86,7 @@ outs = []
 for c, fused in ((ctx, True), (ref_ctx, False)):
     r = c.to_soa(bench.initial_walkers(mol, W, lo))
     _, la = c.log_psi(r)
-    logp = (2.0 * la).contiguous()
+    logp = (2.0 * T(la)).contiguous()
     e_l = torch.empty(W, dtype=torch.float32, device=dev)
     hdr = torch.empty(8, dtype=torch.float64, device=dev)
     gsum = torch.empty(c.P, dtype=torch.float64, device=dev)
@@ -97,7 +99,7 @@ for c, fused in ((ctx, True), (ref_ctx, False)):
             c.walker_step_b(r, e_l, hdr, gsum)
             dist.all_reduce(gsum)
     torch.cuda.synchronize()
-    outs.append((hdr.cpu().numpy().copy(), gsum.cpu().numpy().copy(), r.cpu().numpy().copy()))
+    outs.append((hdr.cpu().numpy().copy(), gsum.cpu().numpy().copy(), np.array(r.cpu().numpy())))
 (h1, g1, r1), (h2, g2, r2) = outs
 eh = np.abs(h1 - h2).max() / np.abs(h2).max()
 eg = np.abs(g1 - g2).max() / np.abs(g2).max()

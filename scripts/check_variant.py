@@ -7,7 +7,6 @@ import sys
 R = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path[:0] = [R, os.path.join(R, "tests"), os.path.join(R, "neural-qmc-wavefunction_b200")]
 import numpy as np  # noqa: E402
-import torch  # noqa: E402
 from _util import make_case, make_context, make_oracle, rel_err  # noqa: E402
 
 s, net, theta, r = make_case(n_atoms=4, hidden=64, W=1000)
@@ -25,8 +24,7 @@ O = o.grad_log_psi(th64, r64)
 wgt = np.random.default_rng(5).standard_normal(1000).astype(np.float32)
 ref = (wgt.astype(np.float64)[:, None] * O).sum(0)
 scale = (np.abs(wgt)[:, None] * np.abs(O)).sum(0)
-got = ctx.grad_accum(soa, torch.as_tensor(wgt).cuda()).cpu().numpy()
-torch.cuda.synchronize()
+got = ctx.grad_accum(soa, ctx.upload(wgt)).cpu().numpy()
 err_g = np.abs(got - ref) / np.maximum(scale, 1e-3)
 print(f"E_L rel err median {np.median(err_e):.2e} max {err_e.max():.2e}; log|psi| max {err_l.max():.2e}; "
       f"grad median {np.median(err_g):.2e} p99 {np.quantile(err_g, .99):.2e} max {err_g.max():.2e}")

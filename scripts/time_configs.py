@@ -8,7 +8,7 @@ sys.path[:0] = [R, os.path.join(R, "tests"), os.path.join(R, "neural-qmc-wavefun
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from oracle.layout import OracleNet, hydrogen_chain_system, init_theta  # noqa: E402
-from _util import make_context  # noqa: E402
+from _util import T, make_context  # noqa: E402
 
 CASES = [("configs[1] H4 64-wide", 4, 64, 65536, False, False),
          ("configs[2] H6 +backflow +cusp, 128-wide", 6, 128, 32768, True, True),
@@ -24,7 +24,7 @@ for name, n_atoms, hidden, W, cusp, bf in CASES:
     r = (s.R[np.arange(s.n_elec) % s.n_atoms][None] + 0.5 * rng.standard_normal((W, s.n_elec, 3))).astype(np.float32)
     soa = ctx.to_soa(r)
     _, la = ctx.log_psi(soa)
-    logp = (2 * la).contiguous()
+    logp = (2 * T(la)).contiguous()
     dev = ctx.dev()
     e_l = torch.empty(W, dtype=torch.float32, device=dev)
     hdr = torch.empty(8, dtype=torch.float64, device=dev)

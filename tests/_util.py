@@ -30,8 +30,18 @@ def make_case(n_atoms=4, hidden=64, kind=KIND_ANTISYMMETRIC, use_cusp=False, W=5
 def make_context(s, net):
     from nqmc_b200 import _native
     return _native.Context(s.R, s.Z, s.n_up, s.n_dn, s.v_nn, kind=net.kind, hidden=net.hidden, use_cusp=net.use_cusp,
-                           use_backflow=net.use_backflow, envelope_decay=net.envelope_decay,
+                           use_backflow=net.use_backflow, envelope_decay=net.envelope_decay, activation=net.activation,
                            cusp_same=net.cusp_same, cusp_diff=net.cusp_diff)
+
+
+def T(x):
+    """DeviceArray -> torch CUDA tensor sharing its memory (tests only; the product never imports torch)."""
+    import torch
+    if isinstance(x, torch.Tensor):
+        return x
+    t = torch.as_tensor(x, device=torch.device("cuda", x.device))
+    t._nqmc_keepalive = x
+    return t
 
 
 def rel_err(a, b):

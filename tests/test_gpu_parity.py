@@ -13,7 +13,7 @@ from oracle.layout import KIND_ANTISYMMETRIC, KIND_SIMPLE
 from oracle.nqmc_oracle import Oracle
 from oracle import philox
 
-from _util import make_case, make_context, make_oracle, rel_err
+from _util import T, make_case, make_context, make_oracle, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -274,7 +274,7 @@ def test_node_hit_is_counted_not_propagated():
     dev = ctx.dev()
     soa = ctx.to_soa(r)
     _, la = ctx.log_psi(soa)
-    logp = (2 * la).contiguous()
+    logp = (2 * T(la)).contiguous()
     e_l = torch.empty(256, dtype=torch.float32, device=dev)
     hdr = torch.empty(8, dtype=torch.float64, device=dev)
     gsum = torch.empty(ctx.P, dtype=torch.float64, device=dev)
