@@ -179,6 +179,15 @@ enum {
 /* hdr[0..7] from e_l[W] (N_ACCEPT left 0).  Replaces jnp.mean / jnp.std in vmc.py:113-114. */
 int nqmc_energy_stats(nqmc_ctx* ctx, const float* e_l, int64_t W, double* hdr, nqmc_stream stream);
 
+/* Blocked statistics for honest error bars: e_l holds n_samples consecutive local energies of
+ * each of W independent chains, sample-major (e_l[s * W + w], the layout nqmc_sample + nqmc_local_energy produce).
+ * Every chain is cut into n_blocks blocks of n_samples / n_blocks samples; out3 = {number of finite block means,
+ * their sum, the sum of their squares}: mean = out3[1]/out3[0], std_error = sqrt(var / out3[0]).
+ * Batched form of the [SPEC] blocking_analysis, .github/phase5-issue-body.md:113-132; n_blocks == n_samples gives the
+ * reference's naive jnp.std / sqrt(n) (src/nqmc/optimizer/vmc.py:114), which ignores autocorrelation. */
+int nqmc_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t n_samples, int64_t W, int32_t n_blocks, double* out3,
+                       nqmc_stream stream);
+
 /* The fused walker step = one sample of VMCOptimizer.step's inner work (vmc.py:242-253):
  *   phase A (nqmc_walker_step_a): MH move (as nqmc_mh_step) -> E_L at the new position -> hdr.
  *   [multi-GPU: the caller all-reduces hdr (8 doubles) here -- the only exchange before phase B]
@@ -238,6 +247,12 @@ int nqmc_comm_active(const nqmc_ctx* ctx); /* 1 once nqmc_comm_attach succeeded 
 /* In-place sum over ranks of vec[0..len), len <= max(param_count, NQMC_HDR_SIZE). */
 int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream stream);
 
+
+/* ---- XLA FFI (csrc/nqmc_xla_ffi.cu) ------------------------------------------------------------------------
+ * 1 when the library was built with the jaxlib headers on the include path and exports the custom-call handler
+ * symbols NqmcLogPsi / NqmcMhStep / NqmcLocalEnergy / NqmcWalkerStep (XLA_FFI_DEFINE_HANDLER_SYMBOL); 0 otherwise
+ * (this image: no jaxlib).  INTEGRATION.md section 4 shows the jax.ffi registration. */
+int nqmc_xla_ffi_available(void);
 
 /* ---- device memory, pinned host memory, streams ------------------------------------------------------------
  * The reference lets JAX own every array.  A host that has no array library of its own (the north_star's

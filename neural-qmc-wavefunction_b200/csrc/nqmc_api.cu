@@ -310,6 +310,7 @@ int nqmc_set_params(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream st
     return NQMC_ERR_ARG;
   }
   NQMC_CUDA(cudaSetDevice(ctx->device));
+  ctx->theta_dirty = true;
   NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyDeviceToDevice, S(st)));
   return NQMC_OK;
 }
@@ -321,6 +322,7 @@ int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stre
     return NQMC_ERR_ARG;
   }
   NQMC_CUDA(cudaSetDevice(ctx->device));
+  ctx->theta_dirty = true;
   NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyHostToDevice, S(st)));
   NQMC_CUDA(cudaStreamSynchronize(S(st)));
   return NQMC_OK;
@@ -523,6 +525,13 @@ int nqmc_energy_stats(nqmc_ctx* ctx, const float* e_l, int64_t W, double* hdr, n
   if (!e_l || !hdr) return NQMC_ERR_ARG;
   NQMC_CUDA(cudaSetDevice(ctx->device));
   return nq_launch_stats(ctx, e_l, nullptr, W, hdr, S(st));
+}
+
+int nqmc_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t n_samples, int64_t W, int32_t n_blocks, double* out3,
+                       nqmc_stream st) {
+  if (!ctx || !e_l || !out3 || n_samples < 1 || W < 1 || n_blocks < 1 || n_blocks > n_samples) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  return nq_blocked_stats(ctx, e_l, n_samples, W, n_blocks, out3, S(st));
 }
 
 int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms,

@@ -17,6 +17,7 @@
 //   Parity = epoch & 1.  Slot reuse is safe with two parities: a peer can only start epoch e+2 after it
 //   finished epoch e+1, which needed this rank's e+1 words, which this rank sent after it had finished
 //   reading the epoch-e inbox (stream order).
+#include <cstdlib>
 #include <cstring>
 
 #include "nqmc_internal.cuh"
@@ -39,8 +40,10 @@ __device__ __forceinline__ void ld_sys_v2u64(const unsigned long long* p, unsign
 // One element per thread; CTA c owns elements [256 c, 256 c + 256) on every rank, so no grid-wide synchronisation
 // is needed.  All loads of a poll round are independent (one L2 latency per round, not one per word).
 __global__ void __launch_bounds__(256) allreduce_f64_kernel(double* __restrict__ vec, const int64_t len, const CommDev c,
-                                                            const unsigned long long epoch) {
+                                                            const unsigned long long epoch, const long long budget,
+                                                            int* __restrict__ timeout_flag) {
   const int par = (int)(epoch & 1ull);
+  const long long t_start = clock64();
   const unsigned long long tag = ((epoch + 1ull) & 0xffffffffull) << 32;
   constexpr unsigned long long HI = 0xffffffff00000000ull, LO = 0xffffffffull;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
@@ -65,6 +68,14 @@ __global__ void __launch_bounds__(256) allreduce_f64_kernel(double* __restrict__
 #pragma unroll
       for (int q = 0; q < MAX_WORLD; ++q)
         if (q < c.world) all = all && (a[q] & HI) == tag && (b[q] & HI) == tag;
+      // bounded spin: a peer that never makes this call (crashed, or issued a different number of exchanges) must not
+      // hang this GPU in a kernel only a device reset clears.  On time-out raise the host-visible flag and leave NaN.
+      if (!all && clock64() - t_start > budget) {
+        *timeout_flag = 1;
+        __threadfence_system();
+        vec[i] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+      }
     } while (!all);
     double s = 0.0;
 #pragma unroll
@@ -83,6 +94,8 @@ struct nq_comm {
   void* peer[MAX_WORLD] = {};            // mapped peers (peer[rank] == local)
   bool attached = false;
   unsigned long long epoch = 0;
+  int* timeout_flag = nullptr;           // pinned, mapped host int the kernel raises when its spin budget runs out
+  long long budget_cycles = 20000000000ll;   // ~10 s at 1.965 GHz (NQMC_COMM_TIMEOUT_MS overrides)
 };
 
 void nq_comm_free(nqmc_ctx* ctx) {
@@ -91,6 +104,7 @@ void nq_comm_free(nqmc_ctx* ctx) {
   for (int q = 0; q < c->world; ++q)
     if (q != c->rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
   if (c->local) cudaFree(c->local);
+  if (c->timeout_flag) cudaFreeHost(c->timeout_flag);
   delete c;
   ctx->comm = nullptr;
 }
@@ -109,6 +123,9 @@ int nq_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out) {
   const size_t bytes = sizeof(unsigned long long) * 2 * 2 * (size_t)world * (size_t)c->len_max;
   NQMC_CUDA(cudaMalloc(&c->local, bytes));
   NQMC_CUDA(cudaMemset(c->local, 0, bytes));
+  NQMC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->timeout_flag), sizeof(int), cudaHostAllocMapped));
+  *c->timeout_flag = 0;
+  if (const char* e = getenv("NQMC_COMM_TIMEOUT_MS")) c->budget_cycles = (long long)(atof(e) * 1.965e6);
   NQMC_CUDA(cudaDeviceSynchronize());
   c->peer[rank] = c->local;
   cudaIpcMemHandle_t h;
@@ -141,6 +158,11 @@ int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st) 
   }
   if (len <= 0 || len > c->len_max || !vec) return NQMC_ERR_ARG;
   if (c->world == 1) return NQMC_OK;
+  if (*static_cast<volatile int*>(c->timeout_flag)) {
+    ctx->err = "peer-memory all-reduce timed out in an earlier call: a rank did not make the matching call "
+               "(all ranks must issue the same exchanges in the same order); destroy the contexts and re-attach";
+    return NQMC_ERR_STATE;
+  }
   CommDev d;
   for (int q = 0; q < MAX_WORLD; ++q) {
     d.inbox[q] = q < c->world ? reinterpret_cast<unsigned long long*>(c->peer[q]) : nullptr;
@@ -150,7 +172,9 @@ int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st) 
   d.len_max = c->len_max;
   int n_cta = (int)((len + 255) / 256);
   if (n_cta > MAX_CTA) n_cta = MAX_CTA;
-  allreduce_f64_kernel<<<n_cta, 256, 0, st>>>(vec, len, d, c->epoch);
+  int* flag_dev = nullptr;
+  NQMC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flag_dev), c->timeout_flag, 0));
+  allreduce_f64_kernel<<<n_cta, 256, 0, st>>>(vec, len, d, c->epoch, c->budget_cycles, flag_dev);
   c->epoch++;
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

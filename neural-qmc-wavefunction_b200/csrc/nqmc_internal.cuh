@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nqmc_b200.h"
@@ -100,6 +101,7 @@ struct nqmc_ctx {
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
   const float* sigma_dev = nullptr;       // device-resident proposal width (set by nqmc_sample while it runs)
+  bool theta_dirty = true;                // a theta writer was enqueued since the last PDL-attributed launch (see nq_launch_pdl)
   // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
   bool prof_on = false;
   static constexpr int PROF_KINDS = 6, PROF_RING = 512;
@@ -208,6 +210,10 @@ int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const doubl
 // predecessor in the stream is still draining (once every CTA of the predecessor has called nq_pdl_trigger or
 // exited); it must call nq_pdl_wait() before touching anything a predecessor wrote.  Used so that the per-CTA weight
 // staging of the tensor-core kernels (reads theta only) overlaps the small kernel in front of them.
+// INVARIANT: such a kernel reads ctx->theta BEFORE nq_pdl_wait(), so the kernel directly in front of it in the stream
+// must not write theta.  The only writers are adam_apply_kernel (nqmc_adam_step) and the set_params copies; both set
+// ctx->theta_dirty, and nq_launch_pdl_guarded() launches WITHOUT the PDL attribute (full stream serialisation) while
+// it is set, clearing it afterwards.
 template <typename... KArgs, typename... Args>
 inline cudaError_t nq_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -222,6 +228,17 @@ inline cudaError_t nq_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+// PDL launch that honours the theta invariant above.
+template <typename... KArgs, typename... Args>
+inline cudaError_t nq_launch_pdl_guarded(nqmc_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, Args&&... args) {
+  if (ctx->theta_dirty) {
+    ctx->theta_dirty = false;
+    kern<<<grid, block, smem, st>>>(KArgs(args)...);
+    return cudaGetLastError();
+  }
+  return nq_launch_pdl(kern, grid, block, smem, st, std::forward<Args>(args)...);
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ void nq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void nq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -233,6 +250,7 @@ int nq_comm_attach(nqmc_ctx* ctx, const void* handles);
 int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st);
 bool nq_comm_active(const nqmc_ctx* ctx);
 void nq_comm_free(nqmc_ctx* ctx);
+int nq_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t S, int64_t W, int n_blocks, double* out, cudaStream_t st);
 int nq_adapt_sigma(nqmc_ctx* ctx, float* n_acc, int64_t W, int steps, float target, float gain, float* sigma_dev,
                    cudaStream_t st);
 int nq_aos_soa(nqmc_ctx* ctx, const float* src, float* dst, int64_t W, bool to_soa, cudaStream_t st);
@@ -248,7 +266,6 @@ int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cud
 int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
 int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                        int64_t W, double* out, cudaStream_t st);
-int nq_launch_orb_eval5_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                          int* n_chunks_out, cudaStream_t st);
 int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
@@ -258,5 +275,4 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
 int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,
                              cudaStream_t st);
 int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st);
-int nq_launch_orb_lap_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
 int nq_launch_orb_lap_pc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);

@@ -770,11 +770,7 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
     if (H == 128) return launch_eval_t<128, 1, 8, 256>(ctx, r, W, phi, st);
   } else if (channels == 5) {
     if (ctx->use_tc) {
-      static const bool lap2 = []() { const char* e = getenv("NQMC_LAP_TC"); return e == nullptr || atoi(e) != 0; }();
-      static const bool lap3 = []() { const char* e = getenv("NQMC_LAP_PC"); return e == nullptr || atoi(e) != 0; }();
-      int rc = lap3 ? nq_launch_orb_lap_pc(ctx, r, W, phi, st) : NQMC_ERR_UNSUPPORTED;   // producer/consumer pipeline
-      if (rc == NQMC_ERR_UNSUPPORTED && lap2) rc = nq_launch_orb_lap_tc(ctx, r, W, phi, st);   // A operand in TMEM, lockstep
-      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_eval5_tc(ctx, r, W, phi, st);   // A operand in shared memory
+      const int rc = nq_launch_orb_lap_pc(ctx, r, W, phi, st);   // tcgen05 producer/consumer pipeline
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
     if (H == 32) return launch_eval_t<32, 5, 4, 256>(ctx, r, W, phi, st);

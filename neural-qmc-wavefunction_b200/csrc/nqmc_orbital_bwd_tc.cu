@@ -648,7 +648,7 @@ int launch_t(nqmc_ctx* ctx, const SmemMap& mp, const float* r, const float* wgt,
       orb_bwd_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, mp.total, st>>>(s, ctx->theta, r, ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp,
                                                                        n_chunks, ctx->p_mlp);
     else
-      NQMC_CUDA(nq_launch_pdl(orb_bwd_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), (size_t)mp.total, st, s, ctx->theta, r,
+      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_bwd_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), (size_t)mp.total, st, s, ctx->theta, r,
                               ctx->inv, wgt, hdr, e_l, W, ctx->part_mlp, n_chunks, ctx->p_mlp));
   }
   NQMC_LAUNCH_CHECK();

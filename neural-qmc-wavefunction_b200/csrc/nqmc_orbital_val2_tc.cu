@@ -336,7 +336,7 @@ int nq_launch_orb_eval1_l1tc(nqmc_ctx* ctx, const float* r, int64_t W, float* ph
   {
     ProfScope ps(ctx, NQ_PROF_EVAL1, st);
     if (ctx->prof_on) orb_eval1_l1tc_kernel<<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
-    else NQMC_CUDA(nq_launch_pdl(orb_eval1_l1tc_kernel, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
+    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_eval1_l1tc_kernel, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

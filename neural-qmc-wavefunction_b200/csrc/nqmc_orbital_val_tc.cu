@@ -287,7 +287,7 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, int n_chunks,
   {
     ProfScope ps(ctx, NQ_PROF_EVAL1, st);
     if (ctx->prof_on) orb_eval1_tc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
-    else NQMC_CUDA(nq_launch_pdl(orb_eval1_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
+    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_eval1_tc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

@@ -754,6 +754,32 @@ __global__ void __launch_bounds__(1024) adapt_sigma_kernel(float* __restrict__ n
   }
 }
 
+// Blocked statistics of per-chain energy series ([SPEC] blocking_analysis,
+// .github/phase5-issue-body.md:113-132, batched over chains): e_l[s * W + w], chain w cut into n_blocks blocks of
+// bs = S / n_blocks consecutive samples; out = (number of finite blocks, sum of block means, sum of squares).
+__global__ void __launch_bounds__(256) blocked_stats_kernel(const float* __restrict__ e_l, const int64_t S, const int64_t W,
+                                                            const int n_blocks, double* __restrict__ out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bs = S / n_blocks;
+  double cnt = 0, s1 = 0, s2 = 0;
+  if (w < W)
+    for (int b = 0; b < n_blocks; ++b) {
+      double a = 0;
+      for (int64_t t = 0; t < bs; ++t) a += (double)e_l[((int64_t)b * bs + t) * W + w];
+      a /= (double)bs;
+      if (isfinite(a)) { cnt += 1; s1 += a; s2 += a * a; }
+    }
+  cnt = warp_sum(cnt); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, cnt); atomicAdd(out + 1, s1); atomicAdd(out + 2, s2); }
+}
+
+int nq_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t S, int64_t W, int n_blocks, double* out, cudaStream_t st) {
+  NQMC_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
+  blocked_stats_kernel<<<(unsigned)((W + 255) / 256), 256, 0, st>>>(e_l, S, W, n_blocks, out);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
 int nq_adapt_sigma(nqmc_ctx* ctx, float* n_acc, int64_t W, int steps, float target, float gain, float* sigma_dev,
                    cudaStream_t st) {
   adapt_sigma_kernel<<<1, 1024, 0, st>>>(n_acc, W, (float)steps, target, gain, sigma_dev);
@@ -888,6 +914,7 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
   adam_norm_kernel<<<nblk, 256, 0, st>>>(gsum, hdr, P, ctx->part_walk);
   NQMC_LAUNCH_CHECK();
   const float bc1 = 1.0f - powf(0.9f, (float)count), bc2 = 1.0f - powf(0.999f, (float)count);
+  ctx->theta_dirty = true;                       // see nq_launch_pdl_guarded
   adam_apply_kernel<<<(P + 255) / 256, 256, 0, st>>>(gsum, hdr, ctx->part_walk, nblk, P, ctx->theta, m, v, lr, clip, bc1, bc2,
                                                      norm_out);
   NQMC_LAUNCH_CHECK();

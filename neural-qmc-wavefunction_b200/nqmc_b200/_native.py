@@ -29,10 +29,10 @@ EXPORTS = [
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
     "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
-    "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample",
+    "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
     "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync",
-    "nqmc_mem_last_error",
+    "nqmc_mem_last_error", "nqmc_xla_ffi_available",
 ]
 
 
@@ -103,6 +103,7 @@ def load_library():
     lib.nqmc_comm_allreduce.argtypes = [vp, vp, i64, vp]
     lib.nqmc_comm_active.argtypes = [vp]
     lib.nqmc_sample.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, i64, i64, i64, vp, vp, vp, f32, i64, vp]
+    lib.nqmc_blocked_stats.argtypes = [vp, vp, i64, i64, C.c_int32, vp, vp]
     sz = C.c_size_t
     lib.nqmc_device_count.argtypes = []
     lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
@@ -482,6 +483,13 @@ class Context:
         hdr = self.empty(HDR_SIZE, np.float64)
         self._check(self.lib.nqmc_energy_stats(self.h, _ptr(e_l), W, hdr.ptr, self.stream), "nqmc_energy_stats")
         return hdr
+
+    def blocked_stats(self, e_l, n_samples: int, W: int, n_blocks: int) -> np.ndarray:
+        """(count, sum, sum of squares) of the per-chain block means -- see nqmc_blocked_stats."""
+        out = self.empty(3, np.float64)
+        self._check(self.lib.nqmc_blocked_stats(self.h, _ptr(e_l), int(n_samples), int(W), int(n_blocks), out.ptr,
+                                                self.stream), "nqmc_blocked_stats")
+        return out.numpy(self.stream)
 
     def walker_step_a(self, r_soa, logp, sigma, e_l, hdr, normals=None, uniforms=None, seed=0, step=0, walker_id0=0,
                       n_accepted=None):

@@ -123,6 +123,8 @@ class VMCOptimizer:
     device_update: bool = False     # extension: fused clip + Adam on the GPU, theta stays resident
     adaptive_step: bool = False     # extension: adapt step_size toward target_acceptance in burn-in
     target_acceptance: float = 0.5
+    n_blocks: int = 0               # extension: > 0 adds metrics["energy_std_blocked"], the error
+                                    # bar from n_blocks blocks per chain (autocorrelation-aware; analysis.chain_blocking)
 
     def _local_chains(self) -> Tuple[int, int]:
         rank, ws = parallel.world()
@@ -165,6 +167,7 @@ class VMCOptimizer:
         lo, hi = self._local_chains()
         n_burn = self.n_burn if state.step == 0 else 10                      # vmc.py:247
         W = hi - lo
+        blocked = None
         if self.n_samples == 1 and normals is None and uniforms is None:
             # burn-in, then the library's fused walker step: sampled move + E_L + header + centred reverse pass
             _, sstate, _, _ = sampler.sample_device(key, log_prob_fn, state.sampler_state, 0, n_burn, 1, walker_id0=lo,
@@ -196,6 +199,12 @@ class VMCOptimizer:
             parallel.reduce_over_ranks_(ctx, gsum)
             h = hdr.numpy(ctx.stream)
             rank, ws = parallel.world()
+            if self.n_blocks > 0 and self.n_samples >= self.n_blocks:
+                b3 = ctx.blocked_stats(e, self.n_samples, W, self.n_blocks)
+                if ws > 1:
+                    b3 = parallel.group().all_reduce_sum(b3)
+                bm = b3[1] / max(b3[0], 1.0)
+                blocked = float(np.sqrt(max(b3[2] / max(b3[0], 1.0) - bm * bm, 0.0) / max(b3[0], 1.0)))
             if ws > 1:
                 a = parallel.group().all_reduce_sum(np.array([acc * W, float(W)]))
                 acc = float(a[0] / a[1])
@@ -220,6 +229,8 @@ class VMCOptimizer:
                    "grad_norm": grad_norm, "n_bad": float(n_bad)}
         if self.adaptive_step:
             metrics["step_size"] = float(sampler.step_size)
+        if blocked is not None:
+            metrics["energy_std_blocked"] = blocked
         return new_state, metrics
 
     def train(self, key, wavefunction, params: Params, molecule, n_steps: int, log_every: int = 10,

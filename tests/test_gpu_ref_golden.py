@@ -109,3 +109,87 @@ def test_gradient_estimator(gold):
     else:
         assert err.max() <= 1e-3, err.max()
     assert np.median(err) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference-facing Python API (nqmc_b200.{wavefunction,sampler,optimizer}) against the same fixtures
+def _host_objects(meta, a):
+    """(molecule, wavefunction, params) of the drop-in package for a fixture."""
+    import nqmc_b200 as nqmc
+    from nqmc_b200.params import unravel
+    from nqmc_b200.systems.molecule import Molecule
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction, SimpleWavefunction
+    g = meta["molecule"]
+    n_el = sum(g["spin"])
+    mol = Molecule.from_atoms(["H"] * len(g["charges"]), np.asarray(g["positions"]), spin_polarization=g["spin"][0] - g["spin"][1])
+    assert mol.spin == tuple(g["spin"]) and mol.n_electrons == n_el
+    if meta["kind"] == "simple":
+        wf = SimpleWavefunction(hidden_dims=tuple(meta["hidden"]), activation=meta["activation"],
+                                envelope_decay=meta.get("envelope_decay", 1.0), nuclear_positions=mol.positions)
+        like = wf.init(nqmc.random.PRNGKey(0), np.zeros((n_el, 3)))
+    else:
+        wf = AntisymmetricWavefunction(g["spin"][0], g["spin"][1], tuple(meta["hidden"]), use_cusp=meta["use_cusp"],
+                                       use_backflow=meta["use_backflow"], molecule=mol)
+        like = wf.init(nqmc.random.PRNGKey(0))
+    return mol, wf, unravel(a["theta"], like)
+
+
+def test_host_api_sample_burn_thin(gold):
+    """MetropolisSampler.sample (metropolis.py:149-218) through the drop-in class, on the reference's streams."""
+    import nqmc_b200 as nqmc
+    from nqmc_b200.sampler import MetropolisSampler, SamplerState
+    a, m = gold["a"], gold["meta"]
+    mol, wf, params = _host_objects(m, a)
+    wf.context(mol)
+    W = a["r"].shape[0]
+    st0 = SamplerState(a["r"].astype(np.float32), (2.0 * a["log_psi"]).astype(np.float32), np.zeros(W, np.float32), 0)
+    smp = MetropolisSampler(step_size=m["step_size"])
+    samples, st, rate = smp.sample(nqmc.random.PRNGKey(1), wf.log_prob_fn(params), st0, n_samples=m["n_samples"],
+                                   n_burn=m["n_burn"], n_thin=m["n_thin"], normals=a["smp_normals"], uniforms=a["smp_uniforms"])
+    assert samples.shape == a["smp_samples"].shape and st.n_steps == m["n_samples"] * m["n_thin"]
+    # walkers whose every accept decision matched end at the same place; a decision may flip only inside the band
+    agree = np.all(np.abs(samples - a["smp_samples"]) <= 2e-6, axis=(0, 2, 3))
+    assert agree.mean() >= 0.9, agree.mean()
+    assert np.array_equal(np.asarray(st.n_accepted)[agree], a["smp_final_n_accepted"][agree])
+    assert abs(rate - float(a["smp_acc_rate"])) <= 2.0 / W + (1 - agree.mean())
+    assert np.max(rel_err(np.asarray(st.log_prob)[agree], a["smp_final_logp"][agree])) <= 5e-5
+
+
+VMC_CASES = [n for n in CASE_NAMES if "vmc" in load(n)[0]]
+
+
+@pytest.mark.parametrize("name", VMC_CASES)
+@pytest.mark.parametrize("device_update", [False, True])
+def test_host_api_vmc_step_trajectory(name, device_update):
+    """VMCOptimizer.step (vmc.py:217-282) -- sample, gradient, optax clip + Adam, metrics -- against the parameter
+    trajectory the reference's own class produced on the same streams."""
+    import nqmc_b200 as nqmc
+    from nqmc_b200.optimizer import VMCOptimizer
+    from nqmc_b200.optimizer.vmc import VMCState, _opt_init
+    from nqmc_b200.params import ravel
+    from nqmc_b200.sampler import SamplerState
+    meta, a, s, net = load(name)
+    mol, wf, params = _host_objects(meta, a)
+    v = meta["vmc"]
+    W = a["vmc_init_positions"].shape[0]
+    opt = VMCOptimizer(learning_rate=v["learning_rate"], n_samples=v["n_samples"], n_chains=W, n_burn=v["n_burn"],
+                       step_size=meta["step_size"], clip_grad=v["clip_grad"], device_update=device_update)
+    st = VMCState(params, _opt_init(params), SamplerState(a["vmc_init_positions"].astype(np.float32),
+                                                         a["vmc_init_logp"].astype(np.float32), np.zeros(W, np.float32), 0), 0)
+    key = nqmc.random.PRNGKey(0)
+    for i in range(v["steps"]):
+        st, m = opt.step(key, st, wf, mol, normals=a[f"vmc_normals_{i}"], uniforms=a[f"vmc_uniforms_{i}"])
+        ref = dict(zip(v["metric_keys"], a["vmc_metrics"][i]))
+        th = ravel(st.params).astype(np.float64)
+        d = np.abs(th - a["vmc_theta"][i])
+        tight = i == 0       # later steps: an accept decision may flip once theta differs in the 7th digit
+        assert abs(m["energy"] - ref["energy"]) <= (1e-4 if tight else 5e-2) * max(1.0, abs(ref["energy"])), (i, m, ref)
+        if tight:
+            assert abs(m["energy_std"] - ref["energy_std"]) <= 1e-3 * max(1.0, ref["energy_std"])
+            assert abs(m["acceptance_rate"] - ref["acceptance_rate"]) <= 2.0 / W
+            assert abs(m["grad_norm"] - ref["grad_norm"]) <= 1e-3 * max(1.0, ref["grad_norm"])
+            # Adam's first step is -lr * sign(g): a parameter whose gradient is zero to rounding may land lr away
+            assert np.mean(d <= 1e-5) >= 0.99, np.mean(d <= 1e-5)
+        assert np.median(d) <= (1e-6 if tight else 1e-3)
+        assert d.max() <= 2.5 * v["learning_rate"] * (i + 1)
+    assert st.step == v["steps"] and st.opt_state["count"] == v["steps"]

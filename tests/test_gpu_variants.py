@@ -11,8 +11,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = {
     "default (producer/consumer forward, MN-major reverse)": {},
-    "forward: A in TMEM, lockstep (nqmc_orbital_lap_tc.cu)": {"NQMC_LAP_PC": "0"},
-    "forward: A in shared memory (nqmc_orbital_tc.cu)": {"NQMC_LAP_PC": "0", "NQMC_LAP_TC": "0"},
     "reverse: FP32 FFMA (nqmc_orbital.cu)": {"NQMC_TC_BWD": "0"},
     "value: layer 1 on the FP32 pipe (nqmc_orbital_val_tc.cu)": {"NQMC_VAL_L1TC": "0"},
     "everything FP32 FFMA": {"NQMC_TC": "0"},
