@@ -275,4 +275,5 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
 int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,
                              cudaStream_t st);
 int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st);
+int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st);   // H = 128
 int nq_launch_orb_lap_pc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);

@@ -1,0 +1,446 @@
+// nqmc_orbital_fwd_pc.cu -- orbital forward pass on tcgen05 for hidden width 128 (BASELINE configs 3 and 5): value
+// only (CH = 1, the Metropolis proposal) or value + gradient + Laplacian (CH = 5, the local energy).
+// Reference lines replaced: sampler/metropolis.py:124 (value), hamiltonian/molecular.py:60-64 (dense nested-autodiff
+// Hessian -> forward Laplacian); orbital definition [SPEC] .github/phase2-issue-body.md:78-113.
+//
+// Same producer / consumer pipeline as nqmc_orbital_lap_pc.cu (hidden width 64) -- one orbital network per CTA,
+// 128-row tiles (128 consecutive walkers x one electron), W2 split once per CTA into tf32 hi/lo in shared memory,
+// 16 worker warps (thread = (row, quarter)) computing layer 1 + activation rules for 8 hidden units at a time and
+// storing them as tf32 hi/lo straight into TMEM (the A operand), a 17th warp issuing
+// tcgen05.mma.cta_group::1.kind::tf32 (3 products per fp32-grade product) behind mbarriers -- generalised over the width:
+//   * CH = 5: the accumulators of a 128-row tile would need 5 x 128 = 640 TMEM columns (> 512), so the output units
+//     are processed in NPASS = H / 64 passes of N = 64.  The layer-1 producer work is repeated per pass (layer 1 is
+//     3..7 % of the MACs) and the output-layer partial sums of a row are carried in registers across the passes;
+//   * CH = 1: one pass with N = H;
+//   * more than 6 nuclei: the per-row nucleus features (d, exp(-d), unit vector, 2/d) no longer fit in registers next
+//     to the accumulators.  The four quarter-threads of a row compute them once per tile, each for a quarter of the
+//     nuclei, into a shared-memory table that every chunk reads back with 16-byte loads.
+// TMEM: CH x NT accumulator columns + 2 x (CH channels x 8 units x {hi, lo}) A columns (CH = 5: 480; CH = 1: 160).
+#include "nqmc_internal.cuh"
+
+namespace {
+
+constexpr int NQ = 4;
+constexpr int TCW = 128 * NQ;
+constexpr int NWW = TCW / 32;          // worker warps
+constexpr int TCT = TCW + 128;         // 16 worker warps + the issuer warpgroup (one issuing warp)
+constexpr int ROWS = 128;
+constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
+constexpr int UPT = KC / NQ;           // 2 units per thread per chunk
+
+template <int H, int NA, int CH>
+struct Cfg {
+  static constexpr int NT = CH == 1 ? H : 64;          // output units per pass == UMMA N
+  static constexpr int NPASS = H / NT;
+  static constexpr int NCHUNK = H / KC;
+  static constexpr int EPC = NT / NQ;                  // epilogue columns per thread
+  static constexpr uint32_t C_A = CH * NT;             // first A-staging column
+  static constexpr uint32_t A_LO = CH * KC, A_STRIDE = 2 * CH * KC;
+  static constexpr uint32_t TMEM_COLS = (C_A + 2 * A_STRIDE) <= 256 ? 256 : 512;
+  static constexpr bool FEAT_SMEM = NA > 6;
+  static constexpr int B_K4 = H * 16;                  // bytes between K-groups of 4 (LBO)
+  static constexpr int B_MAT = (H / 4) * B_K4;
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+  static size_t smem_bytes(int F) {
+    return 2 * (size_t)B_MAT + ((size_t)F * H + 3 * H + (NQ - 1) * ROWS * CH) * 4 +
+           (FEAT_SMEM ? (size_t)NA * 2 * ROWS * 16 : 0) + 128;
+  }
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                        uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, l;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 l, %5, 0;\n\t"
+      "@l tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+  asm volatile("{\n\t.reg .pred l;\n\tsetp.ne.b32 l, %1, 0;\n\t"
+               "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(a) & 0xFFFFE000u;
+  lo = __float_as_uint(a - __uint_as_float(hi));
+}
+
+template <int H, int NA, int CH>
+__global__ void __launch_bounds__(TCT, 1)
+    orb_fwd_pc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
+                      float* __restrict__ phi, const int n_chunks) {
+  using C = Cfg<H, NA, CH>;
+  constexpr int NT = C::NT, NPASS = C::NPASS, NCHUNK = C::NCHUNK, EPC = C::EPC;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* Bhi = smem_raw;                                    // [H/4][H n][4]
+  uint8_t* Blo = Bhi + C::B_MAT;
+  float* W1s = reinterpret_cast<float*>(Blo + C::B_MAT);      // [F][H]
+  float* b1s = W1s + s.F * H;
+  float* b2s = b1s + H;
+  float* W3s = b2s + H;
+  float* outS = W3s + H;                                      // [NQ-1][ROWS][CH]
+  float4* featA = reinterpret_cast<float4*>(outS + (NQ - 1) * ROWS * CH);   // [NA][ROWS] {d, e, 2/d, -}   (FEAT_SMEM)
+  float4* featB = featA + (C::FEAT_SMEM ? NA * ROWS : 0);                   // [NA][ROWS] {ux, uy, uz, -}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(featB + (C::FEAT_SMEM ? NA * ROWS : 0));   // full[2], empty[2], dfull, dempty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (ROWS - 1), quarter = (tid >> 7) & (NQ - 1);
+  const bool worker = tid < TCW;
+  const int m = blockIdx.x % s.n_mlp, chunk = blockIdx.x / s.n_mlp;
+  const int spin = m < s.n_up ? 0 : 1;
+  const int korb = spin == 0 ? m : m - s.n_up;
+  const int ns = spin == 0 ? s.n_up : s.n_dn;
+  const int elec0 = spin == 0 ? 0 : s.n_up;
+  const MlpOff off = s.mlp[m];
+  const int F = s.F;
+
+  for (int idx = tid; idx < F * H; idx += TCT) W1s[idx] = theta[off.W1 + idx];
+  for (int q = tid; q < H; q += TCT) {
+    b1s[q] = theta[off.b1 + q];
+    b2s[q] = theta[off.b2 + q];
+    W3s[q] = theta[off.W3 + q];
+  }
+  for (int idx = tid; idx < H * H; idx += TCT) {
+    const int k = idx / H, n = idx % H;
+    uint32_t hi, lo;
+    split_tf32(theta[off.W2 + idx], hi, lo);
+    const int o = (k >> 2) * (H * 4) + n * 4 + (k & 3);
+    reinterpret_cast<uint32_t*>(Bhi)[o] = hi;
+    reinterpret_cast<uint32_t*>(Blo)[o] = lo;
+  }
+  const float b3 = theta[off.b3];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[0])), "r"(NWW));   // full[0]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[1])), "r"(NWW));   // full[1]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2])));              // empty[0]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[3])));              // empty[1]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[4])));              // dfull
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[5])), "r"(NWW));   // dempty
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+  const uint32_t dfull = smem_u32(&bars[4]), dempty = smem_u32(&bars[5]);
+
+  const int64_t nwb = (W + ROWS - 1) / ROWS;
+  const int64_t n_items = nwb * ns;
+  nq_pdl_wait();                              // everything above read theta only; the positions come from the predecessor
+
+  if (!worker) {
+    // =============================== MMA issuer warp =====================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    if (warp != NWW) return;                                  // three warps only complete the warpgroup
+    const uint32_t leader = elect_one();
+    const uint64_t dBh = umma_desc(smem_u32(Bhi), C::B_K4, 128), dBl = umma_desc(smem_u32(Blo), C::B_K4, 128);
+    uint32_t g = 0, ep = 0;                                    // global chunk counter, global pass counter
+    for (int64_t item = chunk; item < n_items; item += n_chunks) {
+#pragma unroll 1
+      for (int pass = 0; pass < NPASS; ++pass, ++ep) {
+        if (ep > 0) mbar_wait(dempty, (ep - 1) & 1);           // accumulators of the previous pass have been read
+        const uint64_t nb = (uint64_t)(((uint32_t)pass * NT * 16) >> 4);   // output units [NT pass, NT pass + NT)
+#pragma unroll 4
+        for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
+          const uint32_t b = g & 1, u = g >> 1;
+          mbar_wait(full0 + 8 * b, u & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t kb = (uint64_t)(((uint32_t)kc * 2 * C::B_K4) >> 4) + nb;
+          const uint32_t abase = tmem_base + C::C_A + C::A_STRIDE * b;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const uint32_t d = tmem_base + (uint32_t)(c * NT);
+            const uint32_t ah = abase + 8u * c, al = ah + C::A_LO;
+            umma_ts(d, ah, dBh + kb, C::IDESC, kc == 0 ? 0u : 1u, leader);
+            umma_ts(d, al, dBh + kb, C::IDESC, 1u, leader);
+            umma_ts(d, ah, dBl + kb, C::IDESC, 1u, leader);
+          }
+          umma_commit(empty0 + 8 * b, leader);
+          if (kc == NCHUNK - 1) umma_commit(dfull, leader);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =============================== worker warps ========================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t g = 0, ep = 0;
+    float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
+    auto fetch = [&](const int64_t item) {
+      int64_t w = (item / ns) * ROWS + row;
+      if (w >= W) w = W - 1;
+      const int e = elec0 + (int)(item % ns);
+      nx = r[(int64_t)(3 * e + 0) * W + w];
+      ny = r[(int64_t)(3 * e + 1) * W + w];
+      nz = r[(int64_t)(3 * e + 2) * W + w];
+    };
+    if (chunk < n_items) fetch(chunk);
+    for (int64_t item = chunk; item < n_items; item += n_chunks) {
+      const int i = (int)(item % ns);
+      const int64_t w0 = (item / ns) * ROWS;
+      const float x = nx, y = ny, z = nz;
+      if (item + n_chunks < n_items) fetch(item + n_chunks);
+      // per nucleus: d, exp(-d), unit vector, 2/d.  With s = wd - e we the five channels of (d, e) contribute
+      //   value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we      (7 FMA per nucleus and unit, not 10)
+      constexpr int NREG = C::FEAT_SMEM ? 1 : NA;
+      float fdd[NREG], fex[NREG], fux[NREG], fuy[NREG], fuz[NREG], fti[NREG];
+      if constexpr (C::FEAT_SMEM) {
+        // every reader of the previous tile's table has passed that tile's quarter-combine barrier
+        for (int a = quarter; a < NA; a += NQ) {
+          const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+          const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float inv = 1.0f / dd;
+          featA[a * ROWS + row] = make_float4(dd, __expf(-dd), 2.0f * inv, 0.f);
+          featB[a * ROWS + row] = make_float4(dx * inv, dy * inv, dz * inv, 0.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TCW) : "memory");
+      } else {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+          const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float inv = 1.0f / dd;
+          fdd[a] = dd; fex[a] = __expf(-dd); fux[a] = dx * inv; fuy[a] = dy * inv; fuz[a] = dz * inv; fti[a] = 2.0f * inv;
+        }
+      }
+      float out[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) out[c] = 0.f;
+#pragma unroll 1
+      for (int pass = 0; pass < NPASS; ++pass, ++ep) {
+#pragma unroll 2
+        for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
+          const int j0 = KC * kc + UPT * quarter;
+          float acc[CH][UPT];
+          {
+            const float2 bv = *reinterpret_cast<const float2*>(b1s + j0);
+            acc[0][0] = bv.x; acc[0][1] = bv.y;
+#pragma unroll
+            for (int c = 1; c < CH; ++c) acc[c][0] = acc[c][1] = 0.f;
+            float ew[UPT] = {0.f, 0.f};                            // sum_a e_a we_a : part of the value and of the Laplacian
+            const float pc[3] = {x, y, z};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float2 wv = *reinterpret_cast<const float2*>(W1s + d * H + j0);
+              acc[0][0] = fmaf(pc[d], wv.x, acc[0][0]);
+              acc[0][1] = fmaf(pc[d], wv.y, acc[0][1]);
+              if constexpr (CH == 5) {
+                acc[1 + d][0] += wv.x;
+                acc[1 + d][1] += wv.y;
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+              const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
+              const float2 we = *reinterpret_cast<const float2*>(W1s + (3 + NA + a) * H + j0);
+              const float wdv[UPT] = {wd.x, wd.y}, wev[UPT] = {we.x, we.y};
+              float dd, ex, ux = 0.f, uy = 0.f, uz = 0.f, ti = 0.f;
+              if constexpr (C::FEAT_SMEM) {
+                const float4 fa = featA[a * ROWS + row];
+                dd = fa.x; ex = fa.y; ti = fa.z;
+                if constexpr (CH == 5) {
+                  const float4 fb = featB[a * ROWS + row];
+                  ux = fb.x; uy = fb.y; uz = fb.z;
+                }
+              } else {
+                dd = fdd[a]; ex = fex[a]; ux = fux[a]; uy = fuy[a]; uz = fuz[a]; ti = fti[a];
+              }
+#pragma unroll
+              for (int u2 = 0; u2 < UPT; ++u2) {
+                ew[u2] = fmaf(ex, wev[u2], ew[u2]);
+                acc[0][u2] = fmaf(dd, wdv[u2], acc[0][u2]);
+                if constexpr (CH == 5) {
+                  const float sv = fmaf(-ex, wev[u2], wdv[u2]);
+                  acc[1][u2] = fmaf(ux, sv, acc[1][u2]);
+                  acc[2][u2] = fmaf(uy, sv, acc[2][u2]);
+                  acc[3][u2] = fmaf(uz, sv, acc[3][u2]);
+                  acc[4][u2] = fmaf(ti, sv, acc[4][u2]);
+                }
+              }
+            }
+#pragma unroll
+            for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules: lap' = tp (lap - 2 h |grad|^2)
+              const float h = nq_tanh(acc[0][u2] + ew[u2]);
+              if constexpr (CH == 5) {
+                const float tp = fmaf(-h, h, 1.0f);
+                const float g2 = fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
+                acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + ew[u2]);
+                acc[1][u2] *= tp; acc[2][u2] *= tp; acc[3][u2] *= tp;
+              }
+              acc[0][u2] = h;
+            }
+          }
+          const uint32_t b = g & 1, u = g >> 1;
+          if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
+          const uint32_t t_hi = tmem_base + lane_base + C::C_A + C::A_STRIDE * b + (uint32_t)(UPT * quarter);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            uint32_t h0, l0, h1, l1;
+            split_tf32(acc[c][0], h0, l0);
+            split_tf32(acc[c][1], h1, l1);
+            tmem_st2(t_hi + 8u * c, h0, h1);
+            tmem_st2(t_hi + 8u * c + C::A_LO, l0, l1);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full0 + 8 * b);
+        }
+        // ---- epilogue of this pass: output units [NT pass, NT pass + NT) ----------------------------------------
+        mbar_wait(dfull, ep & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int sub = 0; sub < EPC / 8; ++sub) {
+          const int c0 = EPC * quarter + 8 * sub;
+          float v[CH][8];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) tmem_ld8(tmem_base + lane_base + (uint32_t)(c * NT + c0), v[c]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (sub == EPC / 8 - 1) {                               // all accumulator reads of this warp are done
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dempty);
+          }
+          const int jb = pass * NT + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float h = nq_tanh(v[0][j] + b2s[jb + j]);
+            const float w3 = W3s[jb + j];
+            out[0] = fmaf(w3, h, out[0]);
+            if constexpr (CH == 5) {
+              const float tp = fmaf(-h, h, 1.0f);
+              const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
+              const float w3tp = w3 * tp;
+              out[1] = fmaf(w3tp, v[1][j], out[1]);
+              out[2] = fmaf(w3tp, v[2][j], out[2]);
+              out[3] = fmaf(w3tp, v[3][j], out[3]);
+              out[4] = fmaf(w3tp, fmaf(-(h + h), g2, v[4][j]), out[4]);
+            }
+          }
+        }
+      }
+      if (quarter != 0) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) outS[((quarter - 1) * ROWS + row) * CH + c] = out[c];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TCW) : "memory");    // workers only: partial outputs of the 4 quarters visible
+      if (quarter == 0) {
+        const int64_t wr = w0 + row;
+        if (wr < W) {
+          const int ent = ent_index(s, spin, i, korb);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            float o = out[c] + (c == 0 ? b3 : 0.f);
+#pragma unroll
+            for (int q = 0; q < NQ - 1; ++q) o += outS[(q * ROWS + row) * CH + c];
+            phi[((int64_t)c * s.n_ent + ent) * W + wr] = o;
+          }
+        }
+      }
+      // outS (and the feature table) are rewritten only after the next tile's first full[] round / feature barrier,
+      // which every worker warp -- including the readers above -- must reach first
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 2, %0;" ::"n"(TCW + 32) : "memory");   // workers + the issuing warp (the idle warps have left)
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+}
+
+template <int H, int NA, int CH>
+int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
+  using C = Cfg<H, NA, CH>;
+  const DevSys& s = ctx->sys;
+  const size_t smem = C::smem_bytes(s.F);
+  if (smem > 227 * 1024) return NQMC_ERR_UNSUPPORTED;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    NQMC_CUDA(cudaFuncSetAttribute(orb_fwd_pc_kernel<H, NA, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int64_t nwb = (W + ROWS - 1) / ROWS;
+  const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
+  int n_chunks = ctx->sm_count / s.n_mlp;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > max_items) n_chunks = (int)max_items;
+  {
+    ProfScope ps(ctx, CH == 1 ? NQ_PROF_EVAL1 : NQ_PROF_EVAL5, st);
+    if (ctx->prof_on)
+      orb_fwd_pc_kernel<H, NA, CH><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    else
+      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
+                                      ctx->theta, r, W, phi, n_chunks));
+  }
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
+template <int CH>
+int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
+  switch (ctx->sys.A) {                // the number of nuclei is a template parameter: the feature loop is unrolled
+    case 1: return launch_t<128, 1, CH>(ctx, r, W, phi, st);
+    case 2: return launch_t<128, 2, CH>(ctx, r, W, phi, st);
+    case 4: return launch_t<128, 4, CH>(ctx, r, W, phi, st);
+    case 6: return launch_t<128, 6, CH>(ctx, r, W, phi, st);
+    case 8: return launch_t<128, 8, CH>(ctx, r, W, phi, st);
+    case 10: return launch_t<128, 10, CH>(ctx, r, W, phi, st);
+    default: return NQMC_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+// Hidden width 128 only; returns NQMC_ERR_UNSUPPORTED otherwise (the caller falls back to the FP32 FFMA kernels).
+int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st) {
+  if (ctx->sys.H != 128) return NQMC_ERR_UNSUPPORTED;
+  if (channels == 1) return dispatch_na<1>(ctx, r, W, phi, st);
+  if (channels == 5) return dispatch_na<5>(ctx, r, W, phi, st);
+  return NQMC_ERR_UNSUPPORTED;
+}

@@ -1,8 +1,8 @@
 // nqmc_orbital_lap_pc.cu -- 5-channel (value, gradient, Laplacian) orbital forward pass on tcgen05, third variant:
 // a producer / consumer pipeline with NO block-wide barrier in the steady state.
 //
-// The two earlier variants (nqmc_orbital_tc.cu: A operand in shared memory; nqmc_orbital_lap_tc.cu: A operand in
-// TMEM) run all 16 worker warps in lockstep through "layer 1 -> stage -> __syncthreads -> MMA -> wait", so the FMA
+// The two earlier variants (A operand in shared memory; A operand in TMEM with lockstep phases -- both removed in
+// round 2) ran all 16 worker warps in lockstep through "layer 1 -> stage -> __syncthreads -> MMA -> wait", so the FMA
 // pipe, the TMEM/shared-memory ports and the tensor pipe are each busy only in their own phase (ncu: issue slots
 // ~55 %, FMA pipe ~39 %, tensor pipe ~23 %).  Here the warps are decoupled with mbarriers:
 //
@@ -17,7 +17,6 @@
 //   The issuer waits dempty before it overwrites the accumulators with the next tile's first chunk.
 //
 // TMEM: 5 x 64 accumulator columns + 2 x (5 channels x 8 units x {hi, lo}) A columns = 480.
-#include <cstdlib>
 #include "nqmc_internal.cuh"
 
 namespace {
@@ -97,7 +96,7 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) 
 template <int NA>
 __global__ void __launch_bounds__(TCT, 1)
     orb_lap_pc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
-                      float* __restrict__ phi, const int n_chunks, const int dbg) {
+                      float* __restrict__ phi, const int n_chunks) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* Bhi = smem_raw;                                    // [H/4][H n][4]
   uint8_t* Blo = Bhi + B_MAT;
@@ -183,10 +182,8 @@ __global__ void __launch_bounds__(TCT, 1)
           const uint32_t d = tmem_base + (uint32_t)(c * H);
           const uint32_t ah = abase + 8u * c, al = ah + A_LO;
           umma_ts(d, ah, dBh + kb, kc == 0 ? 0u : 1u, leader);
-          if (!(dbg & 1)) {
           umma_ts(d, al, dBh + kb, 1u, leader);
           umma_ts(d, ah, dBl + kb, 1u, leader);
-          }
         }
         umma_commit(empty0 + 8 * b, leader);
         if (kc == NCHUNK - 1) umma_commit(dfull, leader);
@@ -242,7 +239,6 @@ __global__ void __launch_bounds__(TCT, 1)
             acc[1 + d][0] += wv.x;
             acc[1 + d][1] += wv.y;
           }
-          if (!(dbg & 2))
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
@@ -272,7 +268,6 @@ __global__ void __launch_bounds__(TCT, 1)
         const uint32_t b = g & 1, u = g >> 1;
         if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
         const uint32_t t_hi = tmem_base + lane_base + C_A + A_STRIDE * b + (uint32_t)(UPT * quarter);
-        if (!(dbg & 4))
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           uint32_t h0, l0, h1, l1;
@@ -302,7 +297,6 @@ __global__ void __launch_bounds__(TCT, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive(dempty);
         }
-        if (dbg & 8) { out[0] += v[0][0] + v[1][1] + v[2][2] + v[3][3] + v[4][4]; } else
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float h = nq_tanh(v[0][j] + b2s[c0 + j]);
@@ -359,10 +353,8 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t 
   if (n_chunks > max_items) n_chunks = (int)max_items;
   {
     ProfScope ps(ctx, NQ_PROF_EVAL5, st);
-    const char* de = getenv("NQMC_DBG");
-    const int dbg = de ? atoi(de) : 0;
-    if (ctx->prof_on) orb_lap_pc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, dbg);
-    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_lap_pc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks, dbg));
+    if (ctx->prof_on) orb_lap_pc_kernel<NA><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_lap_pc_kernel<NA>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
