@@ -86,12 +86,12 @@ int check_w(nqmc_ctx* ctx, int64_t W) {
 }
 
 void free_scratch(nqmc_ctx* c) {
-  void* ptrs[] = {c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
+  void* ptrs[] = {c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
                   c->part_mlp, c->hdr_tmp, c->jas_sums};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  c->x_cur = c->x_prop = c->vvec = nullptr;
+  c->x_cur = c->x_prop = c->vvec = c->gbf = nullptr;
   c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
@@ -261,6 +261,7 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
     NQMC_CUDA(cudaMalloc(&ctx->x_cur, nn * w * f));
     NQMC_CUDA(cudaMalloc(&ctx->x_prop, nn * w * f));
     NQMC_CUDA(cudaMalloc(&ctx->vvec, nn * w * f));
+    NQMC_CUDA(cudaMalloc(&ctx->gbf, 2 * nn * w * f));
   }
   NQMC_CUDA(cudaMalloc(&ctx->inv, n_ent * w * f));
   NQMC_CUDA(cudaMalloc(&ctx->logabs, w * f));
@@ -466,11 +467,19 @@ static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, flo
   ctx->jas_valid_for = nullptr;
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
   if (ctx->sys.use_bf) {
+    // tensor-core route: G_i first, then a 5-channel orbital pass carrying the G-weighted Laplacian (nqmc_backflow.cu)
+    if (ctx->use_tc && (ctx->sys.H == 64 || ctx->sys.H == 128)) {
+      int rc = nq_launch_backflow_xg(ctx, r, W, ctx->x_cur, ctx->gbf, st);
+      if (rc) return rc;
+      rc = nq_launch_orb_fwd_pc(ctx, ctx->x_cur, W, 5, ctx->phi, ctx->gbf, st);
+      if (rc == NQMC_OK) return nq_launch_assemble_bf(ctx, r, W, e_l, parts, 1, st);
+      if (rc != NQMC_ERR_UNSUPPORTED) return rc;
+    }
     int rc = nq_launch_backflow_x(ctx, r, W, ctx->x_cur, st);
     if (rc) return rc;
-    rc = nq_launch_orb_eval(ctx, ctx->x_cur, W, 10, ctx->phi, st);
+    rc = nq_launch_orb_eval(ctx, ctx->x_cur, W, 10, ctx->phi, st);      // FP32 FFMA: value, gradient, Hessian
     if (rc) return rc;
-    return nq_launch_assemble_bf(ctx, r, W, e_l, parts, st);
+    return nq_launch_assemble_bf(ctx, r, W, e_l, parts, 0, st);
   }
   int rc = nq_launch_orb_eval(ctx, r, W, 5, ctx->phi, st);
   if (rc) return rc;

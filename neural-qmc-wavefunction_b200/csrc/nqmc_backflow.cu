@@ -7,6 +7,12 @@
 //     d_mu log|det|  = tr(Phi^-1 d_mu Phi),   d2_mu log|det| = tr(Phi^-1 d2_mu Phi) - tr((Phi^-1 d_mu Phi)^2)
 //     d_mu Phi[i,k]  = g_ik . d_mu x_i
 //     sum_mu d2_mu Phi[i,k] = sum_ab Hess_ik[ab] G_i[ab] + g_ik . Lap x_i,   G_i = sum_mu d_mu x_i d_mu x_i^T
+// Round 2: the orbital pass no longer needs the six Hessian channels.  Only the contraction sum_ab Hess_ik[ab] G_i[ab]
+// enters E_L, and G_i depends on the backflow Jacobian alone, so backflow_xg_kernel computes G_i BEFORE the orbital
+// pass and the orbital kernels propagate the G-weighted Laplacian L_G = sum_ab G_ab d_a d_b forward instead -- it obeys
+// the same layer rules as the ordinary Laplacian (linear: L_G(W^T h) = W^T L_G(h); tanh: t' L_G(u) + t'' grad u^T G grad u)
+// -- i.e. 5 channels (value, gradient, L_G) instead of 10: half the flops, and the 5-channel tensor-core kernels apply.
+// The 10-channel route stays for the FP32 FFMA parity anchor (NQMC_TC=0).
 // One thread owns one walker; pair tables and orbital derivative tables live in per-thread local
 // memory (L1-resident), which is acceptable because this stage is a few % of the orbital GEMM work.
 #include "nqmc_internal.cuh"
@@ -16,7 +22,7 @@ namespace {
 constexpr int WT = 128;
 constexpr int BH = NQMC_BF_H;   // 16
 
-// eta network with derivatives w.r.t. the scalar distance d.  LEVEL 0: eta ; LEVEL 2: eta, eta', eta''
+// eta network with derivatives w.r.t. the scalar distance d.  LEVEL 0: eta ; 1: eta, eta' ; 2: eta, eta', eta''
 template <int LEVEL>
 __device__ __forceinline__ void eta_eval(const float* __restrict__ theta, const MlpOff& o, const float d, float& eta,
                                          float& etap, float& etapp) {
@@ -28,10 +34,10 @@ __device__ __forceinline__ void eta_eval(const float* __restrict__ theta, const 
     const float u = fmaf(w0, d, fmaf(w1, e, theta[o.b1 + j]));
     const float t = nq_tanh(u);
     h[j] = t;
-    if (LEVEL == 2) {
+    if (LEVEL >= 1) {
       const float tp = fmaf(-t, t, 1.f), up = w0 - w1 * e, upp = w1 * e;
       hp[j] = tp * up;
-      hpp[j] = fmaf(tp, upp, -2.f * t * tp * up * up);
+      if (LEVEL == 2) hpp[j] = fmaf(tp, upp, -2.f * t * tp * up * up);
     }
   }
   float m = theta[o.b3], mp = 0.f, mpp = 0.f;
@@ -42,22 +48,21 @@ __device__ __forceinline__ void eta_eval(const float* __restrict__ theta, const 
     for (int j = 0; j < BH; ++j) {
       const float w = theta[o.W2 + j * BH + k];
       u = fmaf(w, h[j], u);
-      if (LEVEL == 2) { up = fmaf(w, hp[j], up); upp = fmaf(w, hpp[j], upp); }
+      if (LEVEL >= 1) up = fmaf(w, hp[j], up);
+      if (LEVEL == 2) upp = fmaf(w, hpp[j], upp);
     }
     const float t = nq_tanh(u), w3 = theta[o.W3 + k];
     m = fmaf(w3, t, m);
-    if (LEVEL == 2) {
+    if (LEVEL >= 1) {
       const float tp = fmaf(-t, t, 1.f);
       mp = fmaf(w3, tp * up, mp);
-      mpp = fmaf(w3, fmaf(tp, upp, -2.f * t * tp * up * up), mpp);
+      if (LEVEL == 2) mpp = fmaf(w3, fmaf(tp, upp, -2.f * t * tp * up * up), mpp);
     }
   }
   const float E = __expf(-0.5f * d);
   eta = m * E;
-  if (LEVEL == 2) {
-    etap = (mp - 0.5f * m) * E;
-    etapp = (mpp - mp + 0.25f * m) * E;
-  }
+  if (LEVEL >= 1) etap = (mp - 0.5f * m) * E;
+  if (LEVEL == 2) etapp = (mpp - mp + 0.25f * m) * E;
 }
 
 // x = r + sum_j eta(r_ij)(r_i - r_j)
@@ -85,6 +90,65 @@ __global__ void __launch_bounds__(WT) backflow_x_kernel(const DevSys s, const fl
     x[(int64_t)(3 * i) * W + w] = ax[i];
     x[(int64_t)(3 * i + 1) * W + w] = ay[i];
     x[(int64_t)(3 * i + 2) * W + w] = az[i];
+  }
+}
+
+// x as above, plus G_i = sum_mu d_mu x_i d_mu x_i^T (symmetric 3x3, packed xx xy xz yy yz zz) for every electron:
+//   d x_i / d r_i = A_i = S_i I + T_i,  S_i = 1 + sum_j eta_ij,  T_i = sum_j kappa_ij u u^T  (kappa = eta' d)
+//   d x_i / d r_j = -(eta_ij I + kappa_ij u u^T)
+//   G_i = A_i^2 + sum_j (eta^2 I + (2 eta kappa + kappa^2) u u^T)
+__global__ void __launch_bounds__(WT) backflow_xg_kernel(const DevSys s, const float* __restrict__ theta,
+                                                         const float* __restrict__ r, const int64_t W,
+                                                         float* __restrict__ x, float* __restrict__ G) {
+  const int64_t w = (int64_t)blockIdx.x * WT + threadIdx.x;
+  if (w >= W) return;
+  const int N = s.N;
+  float px[NQMC_MAX_ELEC], py[NQMC_MAX_ELEC], pz[NQMC_MAX_ELEC], ax[NQMC_MAX_ELEC], ay[NQMC_MAX_ELEC], az[NQMC_MAX_ELEC];
+  float S[NQMC_MAX_ELEC], T[NQMC_MAX_ELEC][6], Gd[NQMC_MAX_ELEC][6];
+  for (int i = 0; i < N; ++i) {
+    px[i] = ax[i] = r[(int64_t)(3 * i) * W + w];
+    py[i] = ay[i] = r[(int64_t)(3 * i + 1) * W + w];
+    pz[i] = az[i] = r[(int64_t)(3 * i + 2) * W + w];
+    S[i] = 1.f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { T[i][c] = 0.f; Gd[i][c] = 0.f; }
+  }
+  for (int i = 0; i < N; ++i)
+    for (int j = i + 1; j < N; ++j) {
+      const float dx = px[i] - px[j], dy = py[i] - py[j], dz = pz[i] - pz[j];
+      const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+      float eta, etap, t2;
+      eta_eval<1>(theta, s.bf, d, eta, etap, t2);
+      ax[i] = fmaf(eta, dx, ax[i]); ay[i] = fmaf(eta, dy, ay[i]); az[i] = fmaf(eta, dz, az[i]);
+      ax[j] = fmaf(-eta, dx, ax[j]); ay[j] = fmaf(-eta, dy, ay[j]); az[j] = fmaf(-eta, dz, az[j]);
+      const float id = 1.0f / d, u[3] = {dx * id, dy * id, dz * id};
+      const float kap = etap * d;
+      S[i] += eta; S[j] += eta;
+      const float off = fmaf(2.0f * eta, kap, kap * kap);
+      int c = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+          const float uu = u[a] * u[b];
+          T[i][c] = fmaf(kap, uu, T[i][c]); T[j][c] = fmaf(kap, uu, T[j][c]);
+          const float g = fmaf(off, uu, (a == b) ? eta * eta : 0.f);
+          Gd[i][c] += g; Gd[j][c] += g;
+          ++c;
+        }
+    }
+  for (int i = 0; i < N; ++i) {
+    x[(int64_t)(3 * i) * W + w] = ax[i];
+    x[(int64_t)(3 * i + 1) * W + w] = ay[i];
+    x[(int64_t)(3 * i + 2) * W + w] = az[i];
+    const float A[6] = {S[i] + T[i][0], T[i][1], T[i][2], S[i] + T[i][3], T[i][4], S[i] + T[i][5]};
+    float* g = G + (int64_t)(6 * i) * W + w;
+    g[0] = Gd[i][0] + A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
+    g[W] = Gd[i][1] + A[0] * A[1] + A[1] * A[3] + A[2] * A[4];
+    g[2 * W] = Gd[i][2] + A[0] * A[2] + A[1] * A[4] + A[2] * A[5];
+    g[3 * W] = Gd[i][3] + A[1] * A[1] + A[3] * A[3] + A[4] * A[4];
+    g[4 * W] = Gd[i][4] + A[1] * A[2] + A[3] * A[4] + A[4] * A[5];
+    g[5 * W] = Gd[i][5] + A[2] * A[2] + A[4] * A[4] + A[5] * A[5];
   }
 }
 
@@ -190,12 +254,13 @@ __device__ void jastrow_cusp_dyn(const DevSys& s, const float* __restrict__ thet
 
 constexpr int MAXP = NQMC_MAX_ELEC * (NQMC_MAX_ELEC - 1) / 2;
 
-// E_L with backflow.  phi holds 10 channels per orbital-matrix entry, evaluated at x(r).
+// E_L with backflow.  phi holds, per orbital-matrix entry evaluated at x(r), either 10 channels (value, gradient,
+// Hessian; gw == 0) or 5 (value, gradient, G-weighted Laplacian; gw == 1).
 __global__ void __launch_bounds__(WT) assemble_bf_kernel(const DevSys s, const float* __restrict__ theta,
                                                          const float* __restrict__ r, const float* __restrict__ phi,
                                                          float* __restrict__ inv_out, float* __restrict__ v_out,
                                                          const int64_t W, float* __restrict__ e_l,
-                                                         float* __restrict__ parts) {
+                                                         float* __restrict__ parts, const int gw) {
   const int64_t w = (int64_t)blockIdx.x * WT + threadIdx.x;
   if (w >= W) return;
   const int N = s.N;
@@ -286,8 +351,10 @@ __global__ void __launch_bounds__(WT) assemble_bf_kernel(const DevSys s, const f
         sx = fmaf(c, g0, sx); sy = fmaf(c, g1, sy); sz = fmaf(c, g2, sz);
         // sum_ab Hess[ab] G[ab] (off-diagonals count twice) + g . Lap x
         const float* G = Gd[e];
-        float hh = phi[eidx + 4 * cs] * G[0] + phi[eidx + 7 * cs] * G[3] + phi[eidx + 9 * cs] * G[5] +
-                   2.0f * (phi[eidx + 5 * cs] * G[1] + phi[eidx + 6 * cs] * G[2] + phi[eidx + 8 * cs] * G[4]);
+        float hh;
+        if (gw) hh = phi[eidx + 4 * cs];                          // the orbital pass already contracted Hess with G
+        else hh = phi[eidx + 4 * cs] * G[0] + phi[eidx + 7 * cs] * G[3] + phi[eidx + 9 * cs] * G[5] +
+                  2.0f * (phi[eidx + 5 * cs] * G[1] + phi[eidx + 6 * cs] * G[2] + phi[eidx + 8 * cs] * G[4]);
         hh += g0 * lapx[e][0] + g1 * lapx[e][1] + g2 * lapx[e][2];
         term1 = fmaf(c, hh, term1);
       }
@@ -480,16 +547,22 @@ __global__ void bf_grads_finish_kernel(const DevSys s, const float* __restrict__
 
 }  // namespace
 
+int nq_launch_backflow_xg(nqmc_ctx* ctx, const float* r, int64_t W, float* x, float* G, cudaStream_t st) {
+  backflow_xg_kernel<<<(unsigned)((W + WT - 1) / WT), WT, 0, st>>>(ctx->sys, ctx->theta, r, W, x, G);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
 int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cudaStream_t st) {
   backflow_x_kernel<<<(unsigned)((W + WT - 1) / WT), WT, 0, st>>>(ctx->sys, ctx->theta, r, W, x);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
 
-int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
+int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, int gw, cudaStream_t st) {
   ProfScope ps(ctx, NQ_PROF_ASSEMBLE, st);
   assemble_bf_kernel<<<(unsigned)((W + WT - 1) / WT), WT, 0, st>>>(ctx->sys, ctx->theta, r, ctx->phi, ctx->inv, ctx->vvec, W,
-                                                                    e_l, parts);
+                                                                    e_l, parts, gw);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }

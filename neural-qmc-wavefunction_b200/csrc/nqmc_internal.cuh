@@ -84,6 +84,7 @@ struct nqmc_ctx {
   float* x_cur = nullptr;      // [3N][cap_w] backflow coordinates of the current positions
   float* x_prop = nullptr;     // [3N][cap_w] backflow coordinates of the proposal
   float* vvec = nullptr;       // [3N][cap_w] v_i = sum_k inv[k,i] grad phi_k(x_i)  (backflow reverse pass)
+  float* gbf = nullptr;        // [6N][cap_w] G_i = sum_mu d_mu x_i d_mu x_i^T (weights of the backflow Laplacian channel)
   float* r_soa = nullptr;      // [3N][cap_w]  (host-entry staging)
   float* nrm_soa = nullptr;    // [3N][cap_w]
   float* aos_stage = nullptr;  // [cap_w][N][3]
@@ -263,7 +264,8 @@ int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
 int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);
 int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st);
 int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cudaStream_t st);
-int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
+int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, int gw, cudaStream_t st);
+int nq_launch_backflow_xg(nqmc_ctx* ctx, const float* r, int64_t W, float* x, float* G, cudaStream_t st);
 int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                        int64_t W, double* out, cudaStream_t st);
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
@@ -275,5 +277,7 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
 int nq_launch_assemble_stats(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, const float* acc_flag, double* hdr,
                              cudaStream_t st);
 int nq_launch_jastrow_from_sums(nqmc_ctx* ctx, const double* hdr, double* out, cudaStream_t st);
-int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st);   // H = 128
+// tcgen05 forward pass (nqmc_orbital_fwd_pc.cu).  G == nullptr: ordinary Laplacian channel (H = 128 only; H = 64 has
+// nqmc_orbital_lap_pc.cu); G != nullptr: [6N][W] weights of the G-weighted Laplacian L_G (backflow), H = 64 or 128.
+int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, const float* G, cudaStream_t st);
 int nq_launch_orb_lap_pc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);

@@ -763,7 +763,7 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
     if (ctx->use_tc) {
       int rc = nq_launch_orb_eval1_l1tc(ctx, r, W, phi, st);                            // both layers on tensor cores (A <= 6)
       if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_eval1_tc(ctx, r, W, phi, st);  // layer 1 on the FP32 pipe
-      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_fwd_pc(ctx, r, W, 1, phi, st);  // hidden width 128
+      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_fwd_pc(ctx, r, W, 1, phi, nullptr, st);  // hidden width 128
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
     if (H == 32) return launch_eval_t<32, 1, 8, 256>(ctx, r, W, phi, st);
@@ -772,7 +772,7 @@ int nq_launch_orb_eval(nqmc_ctx* ctx, const float* r, int64_t W, int channels, f
   } else if (channels == 5) {
     if (ctx->use_tc) {
       int rc = nq_launch_orb_lap_pc(ctx, r, W, phi, st);         // tcgen05 producer/consumer pipeline, width 64
-      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_fwd_pc(ctx, r, W, 5, phi, st);  // width 128: two N = 64 passes
+      if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_fwd_pc(ctx, r, W, 5, phi, nullptr, st);  // width 128: two N = 64 passes
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
     if (H == 32) return launch_eval_t<32, 5, 4, 256>(ctx, r, W, phi, st);

@@ -28,7 +28,7 @@ constexpr int ROWS = 128;
 constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
 constexpr int UPT = KC / NQ;           // 2 units per thread per chunk
 
-template <int H, int NA, int CH>
+template <int H, int NA, int CH, bool GW = false, int NBUF = 2>
 struct Cfg {
   static constexpr int NT = CH == 1 ? H : 64;          // output units per pass == UMMA N
   static constexpr int NPASS = H / NT;
@@ -36,8 +36,10 @@ struct Cfg {
   static constexpr int EPC = NT / NQ;                  // epilogue columns per thread
   static constexpr uint32_t C_A = CH * NT;             // first A-staging column
   static constexpr uint32_t A_LO = CH * KC, A_STRIDE = 2 * CH * KC;
-  static constexpr uint32_t TMEM_COLS = (C_A + 2 * A_STRIDE) <= 256 ? 256 : 512;
-  static constexpr bool FEAT_SMEM = NA > 6;
+  static constexpr uint32_t TMEM_COLS = (C_A + NBUF * A_STRIDE) <= 256 ? 256 : 512;
+  static_assert(C_A + NBUF * A_STRIDE <= 512, "TMEM: accumulators + A staging exceed 512 columns");
+  // value pass: only d and exp(-d) per nucleus (2 NA registers); GW: one more value per nucleus + the six G entries
+  static constexpr bool FEAT_SMEM = CH == 1 ? (NA > 16) : (NA > 6 || (GW && NA > 4));
   static constexpr int B_K4 = H * 16;                  // bytes between K-groups of 4 (LBO)
   static constexpr int B_MAT = (H / 4) * B_K4;
   static constexpr uint32_t IDESC =
@@ -101,11 +103,13 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
-template <int H, int NA, int CH>
+// GW: the fifth channel is the G-weighted Laplacian L_G = sum_ab G_ab d_a d_b (backflow, nqmc_backflow.cu) with
+// G = Gw[(6 e + c) W + w] (packed xx xy xz yy yz zz) per (electron, walker); GW == false is G = identity.
+template <int H, int NA, int CH, bool GW, int NBUF>
 __global__ void __launch_bounds__(TCT, 1)
     orb_fwd_pc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
-                      float* __restrict__ phi, const int n_chunks) {
-  using C = Cfg<H, NA, CH>;
+                      float* __restrict__ phi, const int n_chunks, const float* __restrict__ Gw) {
+  using C = Cfg<H, NA, CH, GW, NBUF>;
   constexpr int NT = C::NT, NPASS = C::NPASS, NCHUNK = C::NCHUNK, EPC = C::EPC;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* Bhi = smem_raw;                                    // [H/4][H n][4]
@@ -117,8 +121,8 @@ __global__ void __launch_bounds__(TCT, 1)
   float* outS = W3s + H;                                      // [NQ-1][ROWS][CH]
   float4* featA = reinterpret_cast<float4*>(outS + (NQ - 1) * ROWS * CH);   // [NA][ROWS] {d, e, 2/d, -}   (FEAT_SMEM)
   float4* featB = featA + (C::FEAT_SMEM ? NA * ROWS : 0);                   // [NA][ROWS] {ux, uy, uz, -}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(featB + (C::FEAT_SMEM ? NA * ROWS : 0));   // full[2], empty[2], dfull, dempty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(featB + (C::FEAT_SMEM ? NA * ROWS : 0));   // full[NBUF], empty[NBUF], dfull, dempty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (ROWS - 1), quarter = (tid >> 7) & (NQ - 1);
@@ -147,12 +151,12 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   const float b3 = theta[off.b3];
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[0])), "r"(NWW));   // full[0]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[1])), "r"(NWW));   // full[1]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2])));              // empty[0]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[3])));              // empty[1]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[4])));              // dfull
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[5])), "r"(NWW));   // dempty
+    for (int b = 0; b < NBUF; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(NWW));   // full[b]
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[NBUF + b])));       // empty[b]
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2 * NBUF])));              // dfull
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[2 * NBUF + 1])), "r"(NWW));   // dempty
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(TCT, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
-  const uint32_t dfull = smem_u32(&bars[4]), dempty = smem_u32(&bars[5]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NBUF]);
+  const uint32_t dfull = smem_u32(&bars[2 * NBUF]), dempty = smem_u32(&bars[2 * NBUF + 1]);
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(TCT, 1)
         const uint64_t nb = (uint64_t)(((uint32_t)pass * NT * 16) >> 4);   // output units [NT pass, NT pass + NT)
 #pragma unroll 4
         for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
-          const uint32_t b = g & 1, u = g >> 1;
+          const uint32_t b = g % NBUF, u = g / NBUF;
           mbar_wait(full0 + 8 * b, u & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t kb = (uint64_t)(((uint32_t)kc * 2 * C::B_K4) >> 4) + nb;
@@ -228,16 +232,32 @@ __global__ void __launch_bounds__(TCT, 1)
       if (item + n_chunks < n_items) fetch(item + n_chunks);
       // per nucleus: d, exp(-d), unit vector, 2/d.  With s = wd - e we the five channels of (d, e) contribute
       //   value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we      (7 FMA per nucleus and unit, not 10)
+      // GW: Laplacian-channel inputs become  L_G d = (tr G - u^T G u)/d =: A ,  L_G e^-d = e (q - A) with q = u^T G u
+      // (G = I: A = 2/d, q = 1), so the channel gets A s + q e we per nucleus.
       constexpr int NREG = C::FEAT_SMEM ? 1 : NA;
-      float fdd[NREG], fex[NREG], fux[NREG], fuy[NREG], fuz[NREG], fti[NREG];
+      float fdd[NREG], fex[NREG], fux[NREG], fuy[NREG], fuz[NREG], fti[NREG], fq[GW ? NREG : 1];
+      float g6[6] = {1.f, 0.f, 0.f, 1.f, 0.f, 1.f};
+      if constexpr (GW) {
+        int64_t wg = w0 + row;
+        if (wg >= W) wg = W - 1;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) g6[c] = Gw[(int64_t)(6 * (elec0 + i) + c) * W + wg];
+      }
+      auto quad = [&](const float a, const float b, const float c) {   // (a,b,c)^T G (a,b,c)
+        return fmaf(g6[0] * a, a, fmaf(g6[3] * b, b, g6[5] * c * c)) +
+               2.0f * fmaf(g6[1] * a, b, fmaf(g6[2] * a, c, g6[4] * b * c));
+      };
+      const float trG = g6[0] + g6[3] + g6[5];
       if constexpr (C::FEAT_SMEM) {
         // every reader of the previous tile's table has passed that tile's quarter-combine barrier
         for (int a = quarter; a < NA; a += NQ) {
           const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
           const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
           const float inv = 1.0f / dd;
-          featA[a * ROWS + row] = make_float4(dd, __expf(-dd), 2.0f * inv, 0.f);
-          featB[a * ROWS + row] = make_float4(dx * inv, dy * inv, dz * inv, 0.f);
+          const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+          const float q = GW ? quad(ux, uy, uz) : 1.0f;
+          featA[a * ROWS + row] = make_float4(dd, __expf(-dd), GW ? (trG - q) * inv : 2.0f * inv, q);
+          featB[a * ROWS + row] = make_float4(ux, uy, uz, 0.f);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TCW) : "memory");
       } else {
@@ -247,6 +267,10 @@ __global__ void __launch_bounds__(TCT, 1)
           const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
           const float inv = 1.0f / dd;
           fdd[a] = dd; fex[a] = __expf(-dd); fux[a] = dx * inv; fuy[a] = dy * inv; fuz[a] = dz * inv; fti[a] = 2.0f * inv;
+          if constexpr (GW) {
+            fq[a] = quad(fux[a], fuy[a], fuz[a]);
+            fti[a] = (trG - fq[a]) * inv;
+          }
         }
       }
       float out[CH];
@@ -257,20 +281,22 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll 2
         for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
           const int j0 = KC * kc + UPT * quarter;
-          float acc[CH][UPT];
+          constexpr int CM = CH == 1 ? 1 : 5;                  // channels computed (CH = 4 exists for timing experiments only)
+          float acc[CM][UPT];
           {
             const float2 bv = *reinterpret_cast<const float2*>(b1s + j0);
             acc[0][0] = bv.x; acc[0][1] = bv.y;
 #pragma unroll
-            for (int c = 1; c < CH; ++c) acc[c][0] = acc[c][1] = 0.f;
+            for (int c = 1; c < CM; ++c) acc[c][0] = acc[c][1] = 0.f;
             float ew[UPT] = {0.f, 0.f};                            // sum_a e_a we_a : part of the value and of the Laplacian
+            float ewq[UPT] = {0.f, 0.f};                           // GW: sum_a q_a e_a we_a (Laplacian channel)
             const float pc[3] = {x, y, z};
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
               const float2 wv = *reinterpret_cast<const float2*>(W1s + d * H + j0);
               acc[0][0] = fmaf(pc[d], wv.x, acc[0][0]);
               acc[0][1] = fmaf(pc[d], wv.y, acc[0][1]);
-              if constexpr (CH == 5) {
+              if constexpr (CM == 5) {
                 acc[1 + d][0] += wv.x;
                 acc[1 + d][1] += wv.y;
               }
@@ -280,22 +306,25 @@ __global__ void __launch_bounds__(TCT, 1)
               const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
               const float2 we = *reinterpret_cast<const float2*>(W1s + (3 + NA + a) * H + j0);
               const float wdv[UPT] = {wd.x, wd.y}, wev[UPT] = {we.x, we.y};
-              float dd, ex, ux = 0.f, uy = 0.f, uz = 0.f, ti = 0.f;
+              float dd, ex, ux = 0.f, uy = 0.f, uz = 0.f, ti = 0.f, qa = 1.f;
               if constexpr (C::FEAT_SMEM) {
                 const float4 fa = featA[a * ROWS + row];
-                dd = fa.x; ex = fa.y; ti = fa.z;
-                if constexpr (CH == 5) {
+                dd = fa.x; ex = fa.y; ti = fa.z; qa = fa.w;
+                if constexpr (CM == 5) {
                   const float4 fb = featB[a * ROWS + row];
                   ux = fb.x; uy = fb.y; uz = fb.z;
                 }
               } else {
                 dd = fdd[a]; ex = fex[a]; ux = fux[a]; uy = fuy[a]; uz = fuz[a]; ti = fti[a];
+                if constexpr (GW) qa = fq[a];
               }
 #pragma unroll
               for (int u2 = 0; u2 < UPT; ++u2) {
-                ew[u2] = fmaf(ex, wev[u2], ew[u2]);
+                const float ewe = ex * wev[u2];
+                ew[u2] += ewe;
+                if constexpr (GW) ewq[u2] = fmaf(qa, ewe, ewq[u2]);
                 acc[0][u2] = fmaf(dd, wdv[u2], acc[0][u2]);
-                if constexpr (CH == 5) {
+                if constexpr (CM == 5) {
                   const float sv = fmaf(-ex, wev[u2], wdv[u2]);
                   acc[1][u2] = fmaf(ux, sv, acc[1][u2]);
                   acc[2][u2] = fmaf(uy, sv, acc[2][u2]);
@@ -307,16 +336,17 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
             for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules: lap' = tp (lap - 2 h |grad|^2)
               const float h = nq_tanh(acc[0][u2] + ew[u2]);
-              if constexpr (CH == 5) {
+              if constexpr (CM == 5) {
                 const float tp = fmaf(-h, h, 1.0f);
-                const float g2 = fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
-                acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + ew[u2]);
+                const float g2 = GW ? quad(acc[1][u2], acc[2][u2], acc[3][u2])
+                                    : fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
+                acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + (GW ? ewq[u2] : ew[u2]));
                 acc[1][u2] *= tp; acc[2][u2] *= tp; acc[3][u2] *= tp;
               }
               acc[0][u2] = h;
             }
           }
-          const uint32_t b = g & 1, u = g >> 1;
+          const uint32_t b = g % NBUF, u = g / NBUF;
           if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
           const uint32_t t_hi = tmem_base + lane_base + C::C_A + C::A_STRIDE * b + (uint32_t)(UPT * quarter);
 #pragma unroll
@@ -353,14 +383,15 @@ __global__ void __launch_bounds__(TCT, 1)
             const float h = nq_tanh(v[0][j] + b2s[jb + j]);
             const float w3 = W3s[jb + j];
             out[0] = fmaf(w3, h, out[0]);
-            if constexpr (CH == 5) {
+            if constexpr (CH >= 4) {
               const float tp = fmaf(-h, h, 1.0f);
-              const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
+              const float g2 = GW ? quad(v[1][j], v[2][j], v[3][j])
+                                  : fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
               const float w3tp = w3 * tp;
               out[1] = fmaf(w3tp, v[1][j], out[1]);
               out[2] = fmaf(w3tp, v[2][j], out[2]);
               out[3] = fmaf(w3tp, v[3][j], out[3]);
-              out[4] = fmaf(w3tp, fmaf(-(h + h), g2, v[4][j]), out[4]);
+              out[CH - 1] = fmaf(w3tp, fmaf(-(h + h), g2, v[CH - 1][j]), out[CH - 1]);
             }
           }
         }
@@ -393,16 +424,16 @@ __global__ void __launch_bounds__(TCT, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
 }
 
-template <int H, int NA, int CH>
-int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
-  using C = Cfg<H, NA, CH>;
+template <int H, int NA, int CH, bool GW = false, int NBUF = 2>
+int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st) {
+  using C = Cfg<H, NA, CH, GW, NBUF>;
   const DevSys& s = ctx->sys;
   const size_t smem = C::smem_bytes(s.F);
   if (smem > 227 * 1024) return NQMC_ERR_UNSUPPORTED;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
-    NQMC_CUDA(cudaFuncSetAttribute(orb_fwd_pc_kernel<H, NA, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NQMC_CUDA(cudaFuncSetAttribute(orb_fwd_pc_kernel<H, NA, CH, GW, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
@@ -413,34 +444,43 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t 
   {
     ProfScope ps(ctx, CH == 1 ? NQ_PROF_EVAL1 : NQ_PROF_EVAL5, st);
     if (ctx->prof_on)
-      orb_fwd_pc_kernel<H, NA, CH><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
+      orb_fwd_pc_kernel<H, NA, CH, GW, NBUF><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, G);
     else
-      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
-                                      ctx->theta, r, W, phi, n_chunks));
+      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH, GW, NBUF>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
+                                      ctx->theta, r, W, phi, n_chunks, G));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
 
-template <int CH>
-int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st) {
+template <int H, int CH, bool GW>
+int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st) {
   switch (ctx->sys.A) {                // the number of nuclei is a template parameter: the feature loop is unrolled
-    case 1: return launch_t<128, 1, CH>(ctx, r, W, phi, st);
-    case 2: return launch_t<128, 2, CH>(ctx, r, W, phi, st);
-    case 4: return launch_t<128, 4, CH>(ctx, r, W, phi, st);
-    case 6: return launch_t<128, 6, CH>(ctx, r, W, phi, st);
-    case 8: return launch_t<128, 8, CH>(ctx, r, W, phi, st);
-    case 10: return launch_t<128, 10, CH>(ctx, r, W, phi, st);
+    case 1: return launch_t<H, 1, CH, GW>(ctx, r, W, phi, G, st);
+    case 2: return launch_t<H, 2, CH, GW>(ctx, r, W, phi, G, st);
+    case 4: return launch_t<H, 4, CH, GW>(ctx, r, W, phi, G, st);
+    case 6: return launch_t<H, 6, CH, GW>(ctx, r, W, phi, G, st);
+    case 8: return launch_t<H, 8, CH, GW>(ctx, r, W, phi, G, st);
+    case 10: return launch_t<H, 10, CH, GW>(ctx, r, W, phi, G, st);
     default: return NQMC_ERR_UNSUPPORTED;
   }
 }
 
 }  // namespace
 
-// Hidden width 128 only; returns NQMC_ERR_UNSUPPORTED otherwise (the caller falls back to the FP32 FFMA kernels).
-int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, cudaStream_t st) {
-  if (ctx->sys.H != 128) return NQMC_ERR_UNSUPPORTED;
-  if (channels == 1) return dispatch_na<1>(ctx, r, W, phi, st);
-  if (channels == 5) return dispatch_na<5>(ctx, r, W, phi, st);
+// Value (channels == 1) or 5-channel pass.  Without G: hidden width 128 only (width 64 has its own kernels).  With G
+// (backflow, G-weighted Laplacian channel): width 64 or 128.  Returns NQMC_ERR_UNSUPPORTED otherwise (the caller falls
+// back to the FP32 FFMA kernels).
+int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, const float* G, cudaStream_t st) {
+  const int H = ctx->sys.H;
+  if (G != nullptr) {
+    if (channels != 5 || 3 + 2 * ctx->sys.A > H) return NQMC_ERR_UNSUPPORTED;
+    if (H == 64 && ctx->sys.A <= 6) return dispatch_na<64, 5, true>(ctx, r, W, phi, G, st);
+    if (H == 128) return dispatch_na<128, 5, true>(ctx, r, W, phi, G, st);
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  if (H != 128) return NQMC_ERR_UNSUPPORTED;
+  if (channels == 1) return dispatch_na<128, 1, false>(ctx, r, W, phi, nullptr, st);
+  if (channels == 5) return dispatch_na<128, 5, false>(ctx, r, W, phi, nullptr, st);
   return NQMC_ERR_UNSUPPORTED;
 }

@@ -148,6 +148,25 @@ def default_device() -> int:
     return 0
 
 
+# Free device blocks kept for reuse, keyed by (device, nbytes).  cudaMalloc / cudaFree cost ~0.1 ms each and cudaFree
+# synchronises the whole device, which would serialise the walker loop on every temporary.  Reuse is safe for work
+# issued on ONE stream per device (every Context call is, in order); callers that spread one device over several
+# streams should keep their own buffers alive instead of relying on temporaries.
+_POOL: Dict[Tuple[int, int], List[int]] = {}
+_POOL_BYTES = [0]
+_POOL_CAP = 8 << 30
+
+
+def empty_cache() -> None:
+    """Return every pooled block to the driver."""
+    lib = load_library()
+    for (dev, _), ptrs in _POOL.items():
+        for p in ptrs:
+            lib.nqmc_dev_free(dev, p)
+    _POOL.clear()
+    _POOL_BYTES[0] = 0
+
+
 class _HostView(np.ndarray):
     """ndarray that also answers ``.numpy()`` / ``.cpu()`` so results read the same whether a caller holds a
     DeviceArray or (in the tests) a torch tensor."""
@@ -174,16 +193,25 @@ class DeviceArray:
         self.device = default_device() if device is None else int(device)
         self._base = _base
         if _ptr is None:
-            p = C.c_void_p()
-            _mem_check(load_library().nqmc_dev_alloc(self.device, self.nbytes, C.byref(p)), "nqmc_dev_alloc")
-            self.ptr, self._owns = int(p.value), True
+            free = _POOL.get((self.device, self.nbytes))
+            if free:
+                self.ptr, self._owns = free.pop(), True
+                _POOL_BYTES[0] -= self.nbytes
+            else:
+                p = C.c_void_p()
+                _mem_check(load_library().nqmc_dev_alloc(self.device, self.nbytes, C.byref(p)), "nqmc_dev_alloc")
+                self.ptr, self._owns = int(p.value), True
         else:
             self.ptr, self._owns = int(_ptr), False
 
     def __del__(self):
         try:
             if self._owns and self.ptr and _lib is not None:
-                _lib.nqmc_dev_free(self.device, self.ptr)
+                if _POOL_BYTES[0] + self.nbytes <= _POOL_CAP:
+                    _POOL.setdefault((self.device, self.nbytes), []).append(self.ptr)
+                    _POOL_BYTES[0] += self.nbytes
+                else:
+                    _lib.nqmc_dev_free(self.device, self.ptr)
                 self.ptr = 0
         except Exception:
             pass
@@ -339,6 +367,7 @@ class Context:
         self.h = h
         self.P = int(self.lib.nqmc_param_count(self.h))
         self.cap = 0
+        self._theta_host = None      # host copy of the resident theta (set_params skips identical uploads)
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -391,6 +420,10 @@ class Context:
     # ------------------------------------------------------------------ parameters
     def set_params(self, theta):
         """theta: numpy float32 (P,) on host, or a device buffer (data_ptr()) of P floats."""
+        if isinstance(theta, np.ndarray) and self._theta_host is not None and theta.shape == self._theta_host.shape \
+                and np.array_equal(theta, self._theta_host):
+            return                                   # already resident (VMCOptimizer binds theta once per iteration)
+        self._theta_host = None
         if hasattr(theta, "data_ptr"):
             if int(np.prod(_shape(theta))) != self.P:
                 raise ValueError(f"theta must have shape ({self.P},)")
@@ -400,15 +433,18 @@ class Context:
             if th.shape != (self.P,):
                 raise ValueError(f"theta must have shape ({self.P},), got {th.shape}")
             self._check(self.lib.nqmc_set_params_host(self.h, th.ctypes.data, self.P, self.stream), "nqmc_set_params_host")
+            self._theta_host = th.copy()
 
     def get_params(self) -> np.ndarray:
         th = np.empty(self.P, dtype=np.float32)
         self._check(self.lib.nqmc_get_params_host(self.h, th.ctypes.data, self.P, self.stream), "nqmc_get_params_host")
+        self._theta_host = th.copy()
         return th
 
     def adam_step(self, gsum, hdr, m, v, count: int, lr: float, clip: float, grad_norm=None):
         """Fused clip + Adam on the device; theta inside the ctx is updated in place."""
         self.reserve(max(self.cap, 1))
+        self._theta_host = None                      # theta changes on the device
         self._check(self.lib.nqmc_adam_step(self.h, _ptr(gsum), _ptr(hdr), _ptr(m), _ptr(v), int(count),
                                             float(lr), float(clip), _ptr(grad_norm), self.stream), "nqmc_adam_step")
 
