@@ -3,8 +3,10 @@
 import collections, csv, subprocess, sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-rep = sys.argv[2] if len(sys.argv) > 2 else f"gpurun_out/prof_{tag}.ncu-rep"
-rows = list(csv.reader(open("gpurun_out/launches.csv")))
+rep = sys.argv[2] if len(sys.argv) > 2 else (f"gpurun_out/{tag}_prof.ncu-rep" if __import__("os").path.exists(f"gpurun_out/{tag}_prof.ncu-rep") else f"gpurun_out/prof_{tag}.ncu-rep")
+import os
+launches = f"gpurun_out/{tag}_launches.csv" if os.path.exists(f"gpurun_out/{tag}_launches.csv") else "gpurun_out/launches.csv"
+rows = list(csv.reader(open(launches)))
 h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr, data = rows[h], rows[h + 1:]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -29,7 +31,7 @@ rr = list(csv.reader(raw.splitlines()))
 hdr, units, body = rr[0], rr[1], rr[2:]
 keep = [i for i, n in enumerate(hdr) if any(s in n for s in (
     "Kernel Name", "gpu__time_duration.sum", "sm__throughput.avg.pct", "pipe_fma", "pipe_lsu.avg.pct", "pipe_xu.avg.pct",
-    "pipe_alu.avg.pct", "pipe_tensor", "issue_active.avg.pct", "warps_active.avg.pct", "registers_per_thread",
+    "pipe_alu.avg.pct", "pipe_tensor_cycles_active", "pipe_tensor_op", "inst_executed_pipe_uniform", "issue_active.avg.pct", "warps_active.avg.pct", "registers_per_thread",
     "occupancy_limit", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput", "bank_conflicts_pipe_lsu_mem_shared.sum",
     "wavefronts_mem_shared.sum", "issue_stalled", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "shared_mem_per_block",
     "launch__grid_size", "launch__block_size", "thread_inst_executed_op_ffma", "lts__t_bytes.sum"))]
