@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NQMC_ABI_VERSION 2
+#define NQMC_ABI_VERSION 3
 
 typedef struct nqmc_ctx nqmc_ctx;
 typedef void* nqmc_stream; /* cudaStream_t */
@@ -209,6 +209,30 @@ int nqmc_walker_step(nqmc_ctx* ctx, float* r, float* logp, const float* normals,
 int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, const float* normals_aos_host,
                           const float* uniforms_host, uint64_t seed, uint64_t step, int64_t walker_id0, float sigma,
                           int64_t W, float* e_l_host, double* hdr_host, double* gsum_host, nqmc_stream stream);
+
+/* ---- Stochastic Reconfiguration ----------------------------------------------------------
+ * C[M][N] = alpha * A B^T + diag * I at fp32-grade accuracy on the tensor cores (tcgen05 kind::tf32, three products
+ * per fp32 product, fp32 accumulation in TMEM), operands streamed by TMA.  A is [M][lda], B is [N][ldb], both with the
+ * contraction index k contiguous (k < K <= lda, ldb); C is [M][ldc].  Operands must be 16-byte aligned with leading
+ * dimensions that are multiples of 4.  symmetric != 0 (B == A, M == N): only tiles touching the upper triangle are
+ * computed and every element is mirrored, so C is exactly symmetric.
+ * Replaces: S = jnp.einsum('ni,nj->ij', O, O) -- [SPEC] .github/phase6-issue-body.md:168 -- with O kept
+ * parameter-major (A = B = O^T, k = sample). */
+int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+              float alpha, float diag, int symmetric, float* C, int64_t ldc, nqmc_stream stream);
+/* One SR update on the device.
+ * Replaces: [SPEC] StochasticReconfiguration.compute_update -- .github/phase6-issue-body.md:150-181:
+ *   O = log_psi_grads - mean ; E = local_energies - mean ; S = O^T O / n + reg I ; f = 2 E^T O / n ;
+ *   delta = -lr * solve(S, f).
+ * Ot   : [P][ld] per-sample log-derivatives, PARAMETER-major (Ot[p][w] = d log|psi(r_w)| / d theta_p), ld >= n,
+ *        ld % 4 == 0; centred IN PLACE (samples whose local energy is not finite are zeroed and leave every sum)
+ * e_l  : [n] local energies ; S: [P][P] fp32 workspace, on return the regularised S ; work: nqmc_sr_workspace_bytes(P)
+ * delta: [P] fp64 update direction (-lr S^-1 f) ; info (may be NULL): [4] = CG iterations, |r|/|f|, converged, |f|
+ * The solve is Jacobi-preconditioned CG (S is SPD for reg > 0) run for at most max_iter iterations or until
+ * |S x - f| <= tol |f|, entirely in-stream (no host synchronisation). */
+int64_t nqmc_sr_workspace_bytes(int64_t P);
+int nqmc_sr_update(nqmc_ctx* ctx, float* Ot, const float* e_l, int64_t P, int64_t n, int64_t ld, float reg, float lr,
+                   int32_t max_iter, double tol, float* S, double* work, double* delta, double* info, nqmc_stream stream);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */

@@ -32,7 +32,7 @@ EXPORTS = [
     "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
     "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync",
-    "nqmc_mem_last_error", "nqmc_xla_ffi_available",
+    "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update",
 ]
 
 
@@ -105,6 +105,10 @@ def load_library():
     lib.nqmc_sample.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, i64, i64, i64, vp, vp, vp, f32, i64, vp]
     lib.nqmc_blocked_stats.argtypes = [vp, vp, i64, i64, C.c_int32, vp, vp]
     sz = C.c_size_t
+    lib.nqmc_gram.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, f32, f32, C.c_int, vp, i64, vp]
+    lib.nqmc_sr_workspace_bytes.argtypes = [i64]
+    lib.nqmc_sr_workspace_bytes.restype = i64
+    lib.nqmc_sr_update.argtypes = [vp, vp, vp, i64, i64, i64, f32, f32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
     lib.nqmc_device_count.argtypes = []
     lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
     lib.nqmc_dev_free.argtypes = [C.c_int, vp]
@@ -600,6 +604,30 @@ class Context:
         tf = C.c_double()
         self._check(self.lib.nqmc_ffma_peak(self.h, reps, C.byref(tf), self.stream), "nqmc_ffma_peak")
         return tf.value
+
+    def gram(self, A, B=None, alpha: float = 1.0, diag: float = 0.0) -> DeviceArray:
+        """alpha * A B^T + diag * I for device arrays A [M][K], B [N][K] (B None: symmetric A A^T) -- nqmc_gram."""
+        M, K = _shape(A)
+        sym = B is None
+        Bm = A if sym else B
+        N = _shape(Bm)[0]
+        if _shape(Bm)[1] != K:
+            raise ValueError("gram: contraction lengths differ")
+        out = self.empty((M, N))
+        self._check(self.lib.nqmc_gram(self.h, _ptr(A), _ptr(Bm), M, N, K, K, K, float(alpha), float(diag), int(sym),
+                                       out.ptr, N, self.stream), "nqmc_gram")
+        return out
+
+    def sr_update(self, Ot, e_l, reg: float, lr: float, max_iter: int = 200, tol: float = 1e-6):
+        """One Stochastic Reconfiguration update (nqmc_sr_update).  Ot: device [P][n] (centred in place), e_l: device [n].
+        Returns (delta [P] fp64 device array, info [4] fp64 device array, S [P][P])."""
+        P, n = _shape(Ot)
+        S = self.empty((P, P))
+        work = self.empty(int(self.lib.nqmc_sr_workspace_bytes(P)) // 8, np.float64)
+        delta, info = self.empty(P, np.float64), self.empty(4, np.float64)
+        self._check(self.lib.nqmc_sr_update(self.h, _ptr(Ot), _ptr(e_l), P, n, n, float(reg), float(lr), int(max_iter),
+                                            float(tol), S.ptr, work.ptr, delta.ptr, info.ptr, self.stream), "nqmc_sr_update")
+        return delta, info, S
 
     def rng_fill(self, W: int, seed: int, step: int, walker_id0: int = 0):
         n, u = self.empty((3 * self.n_elec, W)), self.empty(W)

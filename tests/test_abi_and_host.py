@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/nqmc_b200.h but not exported"
     assert sorted(_native.EXPORTS) == declared
-    assert lib.nqmc_abi_version() == 2
+    assert lib.nqmc_abi_version() == 3
 
 
 def test_no_cpu_fallback():
