@@ -212,5 +212,10 @@ def _slogdet(M):
     return torch.sign(d), torch.log(torch.abs(d))
 
 
+def einsum(spec, *ops):
+    return torch.einsum(spec, *[_t(o) for o in ops])
+
+
 linalg = types.SimpleNamespace(norm=_norm, slogdet=_slogdet, det=lambda M: _det(_t(M)),
+                               solve=lambda A, b: torch.linalg.solve(_t(A), _t(b)),
                                inv=lambda M: torch.linalg.inv(_t(M)))

@@ -97,3 +97,17 @@ def test_host_class_mirrors_the_spec_signature(ctx):
     assert sr.last_info["converged"] == 1.0
     with pytest.raises(ValueError):
         sr.compute_update(g, e[:-1])
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_sr_update_matches_reference_golden(ctx, case):
+    """CUDA path vs the update the reference's own [SPEC] code block produced (tests/golden/make_ref_sr_golden.py)."""
+    import os
+    from nqmc_b200.optimizer import StochasticReconfiguration
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sr_golden.npz"))
+    lr, reg = g[f"{case}_lr_reg"]
+    sr = StochasticReconfiguration(learning_rate=float(lr), regularization=float(reg), context=ctx, tol=1e-9)
+    d = sr.compute_update(g[f"{case}_grads"], g[f"{case}_energies"])
+    ref = g[f"{case}_update"]
+    # fp32 S with condition number up to ~1/reg: 2e-4 of |delta| (fp32 tolerance of the path, north_star: fp32)
+    assert np.linalg.norm(d - ref) <= 2e-4 * np.linalg.norm(ref), (np.linalg.norm(d - ref) / np.linalg.norm(ref), sr.last_info)

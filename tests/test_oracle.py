@@ -192,3 +192,14 @@ def test_backflow_analytic_equals_autodiff_fp64(n_atoms, cusp):
     assert np.max(np.abs(e - e2) / np.maximum(1, np.abs(e2))) < 1e-9
     O, O2 = o.grad_log_psi(th, r), a.grad_log_psi(th, r)
     assert np.max(np.abs(O - O2) / np.maximum(1, np.abs(O2))) < 1e-9
+
+
+def test_sr_oracle_matches_the_executed_spec_block():
+    """oracle/sr.py against tests/golden/ref_sr_golden.npz (made by executing .github/phase6-issue-body.md:140-181)."""
+    import os
+    from oracle.sr import sr_update
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sr_golden.npz"))
+    for c in "abc":
+        lr, reg = g[f"{c}_lr_reg"]
+        d = sr_update(g[f"{c}_grads"], g[f"{c}_energies"], lr, reg)
+        assert np.allclose(d, g[f"{c}_update"], rtol=1e-9, atol=1e-12)
