@@ -88,7 +88,7 @@ int check_w(nqmc_ctx* ctx, int64_t W) {
 void free_scratch(nqmc_ctx* c) {
   void* ptrs[] = {c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
-                  c->part_mlp, c->hdr_tmp, c->jas_sums};
+                  c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   c->x_cur = c->x_prop = c->vvec = c->gbf = nullptr;
@@ -97,6 +97,8 @@ void free_scratch(nqmc_ctx* c) {
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
   c->jas_valid_for = nullptr;
   c->part_mlp = nullptr;
+  c->bw_h = c->bw_d = c->bw_e = c->bw_f = nullptr;
+  c->bw_rows = 0;
   c->cap_w = 0;
 }
 
@@ -282,6 +284,15 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   NQMC_CUDA(cudaMalloc(&ctx->part_walk, (size_t)ctx->n_blk_walk * 16 * sizeof(double)));
   ctx->n_cta_bwd = 2 * ctx->sm_count;
   NQMC_CUDA(cudaMalloc(&ctx->part_mlp, (size_t)ctx->n_cta_bwd * ctx->p_mlp * f));
+  if (s.kind == NQMC_KIND_ANTISYMMETRIC && s.H == 128 && s.F + 1 <= 32) {
+    ctx->bw_rows = nq_bwd128_rows(ctx, W);
+    const size_t per = (size_t)s.n_mlp * 128 * (size_t)ctx->bw_rows * f;
+    NQMC_CUDA(cudaMalloc(&ctx->bw_h, per));
+    NQMC_CUDA(cudaMalloc(&ctx->bw_d, per));
+    NQMC_CUDA(cudaMalloc(&ctx->bw_e, per));
+    NQMC_CUDA(cudaMalloc(&ctx->bw_f, per / 4));
+    NQMC_CUDA(cudaMemset(ctx->bw_f, 0, per / 4));       // feature rows F+1..31 stay zero
+  }
   ctx->cap_w = W;
   return NQMC_OK;
 }

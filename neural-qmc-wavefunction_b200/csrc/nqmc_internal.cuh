@@ -98,6 +98,12 @@ struct nqmc_ctx {
   float* part_mlp = nullptr;   // [n_cta_bwd][P_mlp_max] per-CTA partial weight gradients
   int n_cta_bwd = 0;
   int p_mlp = 0;               // scalars in one orbital network
+  // hidden width 128, tensor-core reverse pass (nqmc_orbital_bwd128.cu): per-row activations, unit-major
+  float* bw_h = nullptr;       // [n_mlp][128][bw_rows] h1
+  float* bw_d = nullptr;       // [n_mlp][128][bw_rows] delta2
+  float* bw_e = nullptr;       // [n_mlp][128][bw_rows] delta1
+  float* bw_f = nullptr;       // [n_mlp][32][bw_rows]  [1 | features]
+  int64_t bw_rows = 0;
   double* hdr_tmp = nullptr;   // [8]
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
@@ -270,6 +276,9 @@ int nq_launch_bf_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const do
                        int64_t W, double* out, cudaStream_t st);
 int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                          int* n_chunks_out, cudaStream_t st);
+int nq_launch_orb_bwd128(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
+                         int* n_chunks_out, cudaStream_t st);      // hidden width 128: three TMA / tcgen05 kernels
+int64_t nq_bwd128_rows(const nqmc_ctx* ctx, int64_t W);
 int nq_launch_orb_eval1_tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);
 int nq_launch_orb_eval1_l1tc(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t st);   // both layers on tensor cores
 int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m, float* v, int64_t count, float lr,

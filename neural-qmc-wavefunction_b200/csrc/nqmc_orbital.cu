@@ -793,7 +793,8 @@ int nq_launch_orb_bwd(nqmc_ctx* ctx, const float* r, const float* wgt, const dou
   const int H = ctx->sys.H;
   if (ctx->use_tc) {
     int nc = 0;
-    int rc = nq_launch_orb_bwd_tc(ctx, r, wgt, hdr_center, e_l, W, &nc, st);
+    int rc = nq_launch_orb_bwd_tc(ctx, r, wgt, hdr_center, e_l, W, &nc, st);                  // hidden width 64: one fused kernel
+    if (rc == NQMC_ERR_UNSUPPORTED) rc = nq_launch_orb_bwd128(ctx, r, wgt, hdr_center, e_l, W, &nc, st);   // width 128
     if (rc == NQMC_OK) {
       dim3 g((ctx->p_mlp + 31) / 32, ctx->sys.n_mlp);
       orb_bwd_reduce_kernel<<<g, 256, 0, st>>>(ctx->sys, ctx->part_mlp, nc, ctx->p_mlp, out);

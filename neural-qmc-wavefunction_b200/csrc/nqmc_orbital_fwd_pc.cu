@@ -28,7 +28,7 @@ constexpr int ROWS = 128;
 constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
 constexpr int UPT = KC / NQ;           // 2 units per thread per chunk
 
-template <int H, int NA, int CH, bool GW = false, int NBUF = 2>
+template <int H, int NA, int CH, bool GW = false, int NBUF = 2, bool BW = false>
 struct Cfg {
   static constexpr int NT = CH == 1 ? H : 64;          // output units per pass == UMMA N
   static constexpr int NPASS = H / NT;
@@ -103,13 +103,25 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
+// BW (reverse-pass mode, CH = 1, H = 128; see nqmc_orbital_bwd128.cu): the value pass of the reverse sweep.  Instead of
+// phi it leaves, for every row (row id = 128 item + row, item = walker block * ns + electron), unit-major and
+// row-contiguous (so the stores are coalesced and the arrays are K-major GEMM operands for the weight-gradient kernel):
+//   hT[m][unit][row] = h1, dT[m][unit][row] = delta2 = seed W3 (1 - h2^2), fT[m][0..F][row] = [1 | features],
+// and accumulates dW3 += seed h2, db3 += seed in registers (flushed into the CTA's slab at the end).
+struct BwdOut {
+  const float* inv; const float* wgt; const double* hdr; const float* e_l;   // seed = weight * inverse-matrix entry
+  float* hT; float* dT; float* fT; float* part;
+  int64_t rows_pad; int p_mlp;
+};
+
 // GW: the fifth channel is the G-weighted Laplacian L_G = sum_ab G_ab d_a d_b (backflow, nqmc_backflow.cu) with
 // G = Gw[(6 e + c) W + w] (packed xx xy xz yy yz zz) per (electron, walker); GW == false is G = identity.
-template <int H, int NA, int CH, bool GW, int NBUF>
+template <int H, int NA, int CH, bool GW, int NBUF, bool BW>
 __global__ void __launch_bounds__(TCT, 1)
     orb_fwd_pc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
-                      float* __restrict__ phi, const int n_chunks, const float* __restrict__ Gw) {
-  using C = Cfg<H, NA, CH, GW, NBUF>;
+                      float* __restrict__ phi, const int n_chunks, const float* __restrict__ Gw, const BwdOut bw) {
+  using C = Cfg<H, NA, CH, GW, NBUF, BW>;
+  static_assert(!BW || (CH == 1 && !GW && !C::FEAT_SMEM && 3 + 2 * NA + 1 <= 32), "reverse-pass mode: value pass, <= 14 nuclei");
   constexpr int NT = C::NT, NPASS = C::NPASS, NCHUNK = C::NCHUNK, EPC = C::EPC;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* Bhi = smem_raw;                                    // [H/4][H n][4]
@@ -216,6 +228,15 @@ __global__ void __launch_bounds__(TCT, 1)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t g = 0, ep = 0;
     float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
+    float nwt = 1.f, ninv = 0.f;                               // BW: weight and inverse-matrix entry of the row
+    float centerf = 0.f;
+    if constexpr (BW) {
+      if (bw.hdr != nullptr) centerf = (float)(bw.hdr[NQMC_HDR_SUM_E] / fmax(bw.hdr[NQMC_HDR_N], 1.0));
+    }
+    float gW3[BW ? C::EPC : 1];
+    float gb3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < (BW ? C::EPC : 1); ++j) gW3[j] = 0.f;
     auto fetch = [&](const int64_t item) {
       int64_t w = (item / ns) * ROWS + row;
       if (w >= W) w = W - 1;
@@ -223,12 +244,24 @@ __global__ void __launch_bounds__(TCT, 1)
       nx = r[(int64_t)(3 * e + 0) * W + w];
       ny = r[(int64_t)(3 * e + 1) * W + w];
       nz = r[(int64_t)(3 * e + 2) * W + w];
+      if constexpr (BW) {
+        nwt = bw.wgt != nullptr ? bw.wgt[w] : (bw.e_l != nullptr ? bw.e_l[w] : 1.0f);
+        ninv = bw.inv[(int64_t)ent_index(s, spin, (int)(item % ns), korb) * W + w];
+      }
     };
     if (chunk < n_items) fetch(chunk);
     for (int64_t item = chunk; item < n_items; item += n_chunks) {
       const int i = (int)(item % ns);
       const int64_t w0 = (item / ns) * ROWS;
       const float x = nx, y = ny, z = nz;
+      float seed = 0.f;
+      if constexpr (BW) {
+        float wt = nwt;
+        if (bw.wgt == nullptr && bw.e_l != nullptr) wt = isfinite(nwt) ? nwt - centerf : 0.f;
+        seed = wt * ninv;
+        if (w0 + row >= W || !isfinite(seed)) seed = 0.f;
+      }
+      const int64_t rid = item * ROWS + row;                   // BW: row id inside this network's scratch arrays
       if (item + n_chunks < n_items) fetch(item + n_chunks);
       // per nucleus: d, exp(-d), unit vector, 2/d.  With s = wd - e we the five channels of (d, e) contribute
       //   value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we      (7 FMA per nucleus and unit, not 10)
@@ -271,6 +304,18 @@ __global__ void __launch_bounds__(TCT, 1)
             fq[a] = quad(fux[a], fuy[a], fuz[a]);
             fti[a] = (trG - fq[a]) * inv;
           }
+        }
+      }
+      if constexpr (BW) {                                        // [1 | x y z | d_a | e_a] of this row, dealt over its four threads
+        float* fr = bw.fT + (int64_t)m * 32 * bw.rows_pad + rid;
+        const float fv[4] = {1.0f, x, y, z};
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if ((f & 3) == quarter) fr[(int64_t)f * bw.rows_pad] = fv[f];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          if (((4 + a) & 3) == quarter) fr[(int64_t)(4 + a) * bw.rows_pad] = fdd[a];
+          if (((4 + NA + a) & 3) == quarter) fr[(int64_t)(4 + NA + a) * bw.rows_pad] = fex[a];
         }
       }
       float out[CH];
@@ -346,6 +391,11 @@ __global__ void __launch_bounds__(TCT, 1)
               acc[0][u2] = h;
             }
           }
+          if constexpr (BW) {
+            float* hr = bw.hT + ((int64_t)m * H + j0) * bw.rows_pad + rid;
+            hr[0] = acc[0][0];
+            hr[bw.rows_pad] = acc[0][1];
+          }
           const uint32_t b = g % NBUF, u = g / NBUF;
           if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
           const uint32_t t_hi = tmem_base + lane_base + C::C_A + C::A_STRIDE * b + (uint32_t)(UPT * quarter);
@@ -382,6 +432,11 @@ __global__ void __launch_bounds__(TCT, 1)
           for (int j = 0; j < 8; ++j) {
             const float h = nq_tanh(v[0][j] + b2s[jb + j]);
             const float w3 = W3s[jb + j];
+            if constexpr (BW) {
+              gW3[8 * sub + j] = fmaf(seed, h, gW3[8 * sub + j]);
+              bw.dT[((int64_t)m * H + jb + j) * bw.rows_pad + rid] = seed * w3 * fmaf(-h, h, 1.0f);
+              continue;
+            }
             out[0] = fmaf(w3, h, out[0]);
             if constexpr (CH >= 4) {
               const float tp = fmaf(-h, h, 1.0f);
@@ -395,6 +450,10 @@ __global__ void __launch_bounds__(TCT, 1)
             }
           }
         }
+      }
+      if constexpr (BW) {
+        if (quarter == 0) gb3 += seed;
+        continue;
       }
       if (quarter != 0) {
 #pragma unroll
@@ -417,6 +476,25 @@ __global__ void __launch_bounds__(TCT, 1)
       // outS (and the feature table) are rewritten only after the next tile's first full[] round / feature barrier,
       // which every worker warp -- including the readers above -- must reach first
     }
+    if constexpr (BW) {                                          // dW3 / db3: reduce the per-row partials over the 128 rows
+      float* red = outS;                                         // [H + 1], unused in this mode
+      for (int q = tid; q < H + 1; q += TCW) red[q] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(TCW) : "memory");
+#pragma unroll
+      for (int j = 0; j < C::EPC; ++j) {
+        const float t = warp_sum(gW3[j]);
+        if (lane == 0) atomicAdd(&red[C::EPC * quarter + j], t);
+      }
+      if (quarter == 0) {
+        const float t = warp_sum(gb3);
+        if (lane == 0) atomicAdd(&red[H], t);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TCW) : "memory");
+      float* slab = bw.part + (int64_t)blockIdx.x * bw.p_mlp;
+      const int o_b3 = 2 * H + F * H + H * H, o_W3 = o_b3 + 1;   // slab order: b1[H] W1[F*H] b2[H] W2[H*H] b3 W3[H]
+      for (int q = tid; q < H; q += TCW) slab[o_W3 + q] = red[q];
+      if (tid == 0) slab[o_b3] = red[H];
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   asm volatile("bar.sync 2, %0;" ::"n"(TCW + 32) : "memory");   // workers + the issuing warp (the idle warps have left)
@@ -424,16 +502,17 @@ __global__ void __launch_bounds__(TCT, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
 }
 
-template <int H, int NA, int CH, bool GW = false, int NBUF = 2>
-int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st) {
-  using C = Cfg<H, NA, CH, GW, NBUF>;
+template <int H, int NA, int CH, bool GW = false, int NBUF = 2, bool BW = false>
+int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st, const BwdOut bw = BwdOut{},
+             int n_chunks_forced = 0) {
+  using C = Cfg<H, NA, CH, GW, NBUF, BW>;
   const DevSys& s = ctx->sys;
   const size_t smem = C::smem_bytes(s.F);
   if (smem > 227 * 1024) return NQMC_ERR_UNSUPPORTED;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
-    NQMC_CUDA(cudaFuncSetAttribute(orb_fwd_pc_kernel<H, NA, CH, GW, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NQMC_CUDA(cudaFuncSetAttribute(orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
@@ -441,13 +520,14 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* 
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
+  if (n_chunks_forced > 0) n_chunks = n_chunks_forced;
   {
-    ProfScope ps(ctx, CH == 1 ? NQ_PROF_EVAL1 : NQ_PROF_EVAL5, st);
+    ProfScope ps(ctx, BW ? NQ_PROF_BWD : (CH == 1 ? NQ_PROF_EVAL1 : NQ_PROF_EVAL5), st);
     if (ctx->prof_on)
-      orb_fwd_pc_kernel<H, NA, CH, GW, NBUF><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, G);
+      orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, G, bw);
     else
-      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH, GW, NBUF>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
-                                      ctx->theta, r, W, phi, n_chunks, G));
+      NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
+                                      ctx->theta, r, W, phi, n_chunks, G, bw));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
@@ -467,6 +547,22 @@ int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const floa
 }
 
 }  // namespace
+
+// Reverse-pass value sweep (hidden width 128): see BwdOut.  n_chunks CTAs per network, slab index = blockIdx.x.
+int nq_launch_orb_fwd_bw128(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
+                            float* hT, float* dT, float* fT, int64_t rows_pad, int n_chunks, cudaStream_t st) {
+  if (ctx->sys.H != 128) return NQMC_ERR_UNSUPPORTED;
+  const BwdOut bw{ctx->inv, wgt, hdr, e_l, hT, dT, fT, ctx->part_mlp, rows_pad, ctx->p_mlp};
+  switch (ctx->sys.A) {
+    case 1: return launch_t<128, 1, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    case 2: return launch_t<128, 2, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    case 4: return launch_t<128, 4, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    case 6: return launch_t<128, 6, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    case 8: return launch_t<128, 8, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    case 10: return launch_t<128, 10, 1, false, 2, true>(ctx, r, W, nullptr, nullptr, st, bw, n_chunks);
+    default: return NQMC_ERR_UNSUPPORTED;
+  }
+}
 
 // Value (channels == 1) or 5-channel pass.  Without G: hidden width 128 only (width 64 has its own kernels).  With G
 // (backflow, G-weighted Laplacian channel): width 64 or 128.  Returns NQMC_ERR_UNSUPPORTED otherwise (the caller falls
