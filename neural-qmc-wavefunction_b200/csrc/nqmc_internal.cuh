@@ -161,6 +161,49 @@ __device__ __forceinline__ float nq_tanh(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+// Packed FP32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, each component
+// rounded exactly like the scalar instruction).  The SIMT stages of the tensor-core kernels are issue-bound, and their
+// per-unit math comes in pairs (two hidden units / two accumulator columns per thread), so packing halves the issue
+// slots of that arithmetic.  ptxas folds a duplicated scalar into a broadcast operand.
+__device__ __forceinline__ float2 nq_fma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 nq_mul2(const float2 a, const float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 nq_add2(const float2 a, const float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 nq_bc2(const float a) { return make_float2(a, a); }
+// nq_tanh on a pair: same formula, same roundings (2 * rcp is exact, so fma(-2, rcp, 1) == 1 - __fdividef(2, .))
+__device__ __forceinline__ float2 nq_tanh2(const float2 x) {
+  const float2 t = nq_mul2(x, nq_bc2(2.885390081777927f));
+  const float2 e = nq_add2(make_float2(exp2f(t.x), exp2f(t.y)), nq_bc2(1.0f));
+  float rx, ry;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(e.y));
+  return nq_fma2(nq_bc2(-2.0f), make_float2(rx, ry), nq_bc2(1.0f));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -27,6 +27,7 @@ constexpr int TCT = TCW + 128;         // 16 worker warps + the issuer warpgroup
 constexpr int ROWS = 128;
 constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
 constexpr int UPT = KC / NQ;           // 2 units per thread per chunk
+constexpr int NISS = 4;                // issuing warps (one thread sustains one tcgen05.mma per ~117 cycles; see nqmc_orbital_lap_pc.cu)
 
 template <int H, int NA, int CH, bool GW = false, int NBUF = 2, bool BW = false>
 struct Cfg {
@@ -165,9 +166,9 @@ __global__ void __launch_bounds__(TCT, 1)
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(NWW));   // full[b]
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[NBUF + b])));       // empty[b]
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[NBUF + b])), "r"(NISS));   // empty[b]
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2 * NBUF])));              // dfull
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[2 * NBUF])), "r"(NISS));  // dfull
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[2 * NBUF + 1])), "r"(NWW));   // dempty
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(TCT, 1)
   if (!worker) {
     // =============================== MMA issuer warp =====================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-    if (warp != NWW) return;                                  // three warps only complete the warpgroup
+    const int iw = warp - NWW;                                 // CH = 5: channel c is issued by warp c % NISS; CH = 1: k-steps dealt round-robin
     const uint32_t leader = elect_one();
     const uint64_t dBh = umma_desc(smem_u32(Bhi), C::B_K4, 128), dBl = umma_desc(smem_u32(Blo), C::B_K4, 128);
     uint32_t g = 0, ep = 0;                                    // global chunk counter, global pass counter
@@ -208,8 +209,7 @@ __global__ void __launch_bounds__(TCT, 1)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t kb = (uint64_t)(((uint32_t)kc * 2 * C::B_K4) >> 4) + nb;
           const uint32_t abase = tmem_base + C::C_A + C::A_STRIDE * b;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
+          for (int c = iw; c < CH; c += NISS) {                // a warp without a channel only commits
             const uint32_t d = tmem_base + (uint32_t)(c * NT);
             const uint32_t ah = abase + 8u * c, al = ah + C::A_LO;
             umma_ts(d, ah, dBh + kb, C::IDESC, kc == 0 ? 0u : 1u, leader);
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  asm volatile("bar.sync 2, %0;" ::"n"(TCW + 32) : "memory");   // workers + the issuing warp (the idle warps have left)
+  asm volatile("bar.sync 2, %0;" ::"n"(TCT) : "memory");        // workers + the issuing warps
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
 }

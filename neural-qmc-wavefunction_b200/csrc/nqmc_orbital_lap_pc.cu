@@ -32,6 +32,12 @@ constexpr int KC = 8;                  // units per K-chunk == one UMMA k-step
 constexpr int NCHUNK = H / KC;         // 8
 constexpr int UPT = KC / NQ;           // 2 units per thread per chunk
 constexpr int EPC = H / NQ;            // 16 epilogue columns per thread
+// One thread gets a tcgen05.mma out only every ~117 cycles whatever its shape (scripts/exp/mma_rate.cu: N = 32 ... 192,
+// one or several accumulators), while the tensor pipe needs 32 cycles for an M128 N64 K8 one; several issuing warps
+// scale.  With a single issuer the 120 UMMAs of a tile took 14 k cycles -- the whole tile time.  All four warps of the
+// issuer warpgroup therefore issue, each for its own accumulators (channel c belongs to warp c % 4: the kc == 0
+// overwrite and the accumulating products of one accumulator stay in one thread's program order).
+constexpr int NISS = 4;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t C_A = 320, A_STRIDE = 80, A_LO = 40;   // buffer b: hi at C_A + 80 b + 8 c, lo 40 columns later
 constexpr int B_K4 = H * 16;
@@ -137,9 +143,9 @@ __global__ void __launch_bounds__(TCT, 1)
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[0])), "r"(NWW));   // full[0]
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[1])), "r"(NWW));   // full[1]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2])));              // empty[0]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[3])));              // empty[1]
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[4])));              // dfull
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[2])), "r"(NISS));  // empty[0]: one commit per issuing warp
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[3])), "r"(NISS));  // empty[1]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[4])), "r"(NISS));  // dfull
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[5])), "r"(NWW));   // dempty
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(TCT, 1)
     // =============================== MMA issuer warp =====================================================
     // register split (as in nqmc_orbital_bwd_tc.cu): 20 warps x 96 at launch -> 112 per worker, 32 per issuer thread
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-    if (warp != NWW) return;                                  // three warps only complete the warpgroup
+    const int iw = warp - NWW;                                 // channel c is issued by warp c % NISS
     const uint32_t leader = elect_one();
     const uint64_t dBh = umma_desc(smem_u32(Bhi), B_K4, 128), dBl = umma_desc(smem_u32(Blo), B_K4, 128);
     uint32_t g = 0, t = 0;                                     // global chunk counter, local tile counter
@@ -177,8 +183,7 @@ __global__ void __launch_bounds__(TCT, 1)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t kb = (uint64_t)(((uint32_t)kc * 2 * B_K4) >> 4);
         const uint32_t abase = tmem_base + C_A + A_STRIDE * b;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
+        for (int c = iw; c < CH; c += NISS) {
           const uint32_t d = tmem_base + (uint32_t)(c * H);
           const uint32_t ah = abase + 8u * c, al = ah + A_LO;
           umma_ts(d, ah, dBh + kb, kc == 0 ? 0u : 1u, leader);
@@ -223,58 +228,50 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll 2
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
         const int j0 = KC * kc + UPT * quarter;
-        float acc[CH][UPT];
+        // the thread's two hidden units are one packed pair: every FMA / MUL / ADD below is one FFMA2 / FMUL2 / FADD2
+        float2 acc[CH];
         {
-          const float2 bv = *reinterpret_cast<const float2*>(b1s + j0);
-          acc[0][0] = bv.x; acc[0][1] = bv.y;
-#pragma unroll
-          for (int c = 1; c < CH; ++c) acc[c][0] = acc[c][1] = 0.f;
-          float ew[UPT] = {0.f, 0.f};                            // sum_a e_a we_a : part of the value and of the Laplacian
-          const float pc[3] = {x, y, z};
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const float2 wv = *reinterpret_cast<const float2*>(W1s + d * H + j0);
-            acc[0][0] = fmaf(pc[d], wv.x, acc[0][0]);
-            acc[0][1] = fmaf(pc[d], wv.y, acc[0][1]);
-            acc[1 + d][0] += wv.x;
-            acc[1 + d][1] += wv.y;
-          }
+          acc[0] = *reinterpret_cast<const float2*>(b1s + j0);
+          float2 ew = make_float2(0.f, 0.f);                     // sum_a e_a we_a : part of the value and of the Laplacian
+          acc[0] = nq_fma2(nq_bc2(x), *reinterpret_cast<const float2*>(W1s + 0 * H + j0), acc[0]);
+          acc[1] = *reinterpret_cast<const float2*>(W1s + 0 * H + j0);
+          acc[0] = nq_fma2(nq_bc2(y), *reinterpret_cast<const float2*>(W1s + 1 * H + j0), acc[0]);
+          acc[2] = *reinterpret_cast<const float2*>(W1s + 1 * H + j0);
+          acc[0] = nq_fma2(nq_bc2(z), *reinterpret_cast<const float2*>(W1s + 2 * H + j0), acc[0]);
+          acc[3] = *reinterpret_cast<const float2*>(W1s + 2 * H + j0);
+          acc[4] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
             const float2 we = *reinterpret_cast<const float2*>(W1s + (3 + NA + a) * H + j0);
-            const float wdv[UPT] = {wd.x, wd.y}, wev[UPT] = {we.x, we.y};
-#pragma unroll
-            for (int u2 = 0; u2 < UPT; ++u2) {
-              ew[u2] = fmaf(fex[a], wev[u2], ew[u2]);
-              acc[0][u2] = fmaf(fdd[a], wdv[u2], acc[0][u2]);
-              const float sv = fmaf(-fex[a], wev[u2], wdv[u2]);
-              acc[1][u2] = fmaf(fux[a], sv, acc[1][u2]);
-              acc[2][u2] = fmaf(fuy[a], sv, acc[2][u2]);
-              acc[3][u2] = fmaf(fuz[a], sv, acc[3][u2]);
-              acc[4][u2] = fmaf(fti[a], sv, acc[4][u2]);
-            }
+            ew = nq_fma2(nq_bc2(fex[a]), we, ew);
+            acc[0] = nq_fma2(nq_bc2(fdd[a]), wd, acc[0]);
+            const float2 sv = nq_fma2(nq_bc2(-fex[a]), we, wd);
+            acc[1] = nq_fma2(nq_bc2(fux[a]), sv, acc[1]);
+            acc[2] = nq_fma2(nq_bc2(fuy[a]), sv, acc[2]);
+            acc[3] = nq_fma2(nq_bc2(fuz[a]), sv, acc[3]);
+            acc[4] = nq_fma2(nq_bc2(fti[a]), sv, acc[4]);
           }
-#pragma unroll
-          for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules: lap' = tp (lap - 2 h |grad|^2)
-            const float h = nq_tanh(acc[0][u2] + ew[u2]);
-            const float tp = fmaf(-h, h, 1.0f);
-            const float g2 = fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
-            acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + ew[u2]);
-            acc[1][u2] *= tp; acc[2][u2] *= tp; acc[3][u2] *= tp;
-            acc[0][u2] = h;
-          }
+          // tanh rules: lap' = tp (lap - 2 h |grad|^2)
+          const float2 h = nq_tanh2(nq_add2(acc[0], ew));
+          const float2 tp = nq_fma2(make_float2(-h.x, -h.y), h, nq_bc2(1.0f));
+          const float2 g2 = nq_fma2(acc[1], acc[1], nq_fma2(acc[2], acc[2], nq_mul2(acc[3], acc[3])));
+          acc[4] = nq_mul2(tp, nq_fma2(make_float2(-(h.x + h.x), -(h.y + h.y)), g2, nq_add2(acc[4], ew)));
+          acc[1] = nq_mul2(acc[1], tp);
+          acc[2] = nq_mul2(acc[2], tp);
+          acc[3] = nq_mul2(acc[3], tp);
+          acc[0] = h;
         }
         const uint32_t b = g & 1, u = g >> 1;
         if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
         const uint32_t t_hi = tmem_base + lane_base + C_A + A_STRIDE * b + (uint32_t)(UPT * quarter);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          uint32_t h0, l0, h1, l1;
-          split_tf32(acc[c][0], h0, l0);
-          split_tf32(acc[c][1], h1, l1);
-          tmem_st2(t_hi + 8u * c, h0, h1);
-          tmem_st2(t_hi + 8u * c + A_LO, l0, l1);
+          const float2 hi = make_float2(__uint_as_float(__float_as_uint(acc[c].x) & 0xFFFFE000u),
+                                        __uint_as_float(__float_as_uint(acc[c].y) & 0xFFFFE000u));
+          const float2 lo = nq_add2(acc[c], make_float2(-hi.x, -hi.y));
+          tmem_st2(t_hi + 8u * c, __float_as_uint(hi.x), __float_as_uint(hi.y));
+          tmem_st2(t_hi + 8u * c + A_LO, __float_as_uint(lo.x), __float_as_uint(lo.y));
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -284,7 +281,9 @@ __global__ void __launch_bounds__(TCT, 1)
       // ---- epilogue ------------------------------------------------------------------------------------------
       mbar_wait(dfull, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float out[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      float2 out2[CH];                                         // even / odd columns of this thread, added at the end
+#pragma unroll
+      for (int c = 0; c < CH; ++c) out2[c] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int sub = 0; sub < EPC / 8; ++sub) {
         const int c0 = EPC * quarter + 8 * sub;
@@ -298,18 +297,24 @@ __global__ void __launch_bounds__(TCT, 1)
           if (lane == 0) mbar_arrive(dempty);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float h = nq_tanh(v[0][j] + b2s[c0 + j]);
-          const float tp = fmaf(-h, h, 1.0f);
-          const float g2 = fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
-          const float w3 = W3s[c0 + j], w3tp = w3 * tp;
-          out[0] = fmaf(w3, h, out[0]);
-          out[1] = fmaf(w3tp, v[1][j], out[1]);
-          out[2] = fmaf(w3tp, v[2][j], out[2]);
-          out[3] = fmaf(w3tp, v[3][j], out[3]);
-          out[4] = fmaf(w3tp, fmaf(-(h + h), g2, v[4][j]), out[4]);
+        for (int j = 0; j < 8; j += 2) {                        // two columns per packed instruction
+          const float2 v0 = make_float2(v[0][j], v[0][j + 1]), v1 = make_float2(v[1][j], v[1][j + 1]);
+          const float2 v2 = make_float2(v[2][j], v[2][j + 1]), v3 = make_float2(v[3][j], v[3][j + 1]);
+          const float2 v4 = make_float2(v[4][j], v[4][j + 1]);
+          const float2 h = nq_tanh2(nq_add2(v0, *reinterpret_cast<const float2*>(b2s + c0 + j)));
+          const float2 tp = nq_fma2(make_float2(-h.x, -h.y), h, nq_bc2(1.0f));
+          const float2 g2 = nq_fma2(v1, v1, nq_fma2(v2, v2, nq_mul2(v3, v3)));
+          const float2 w3 = *reinterpret_cast<const float2*>(W3s + c0 + j), w3tp = nq_mul2(w3, tp);
+          out2[0] = nq_fma2(w3, h, out2[0]);
+          out2[1] = nq_fma2(w3tp, v1, out2[1]);
+          out2[2] = nq_fma2(w3tp, v2, out2[2]);
+          out2[3] = nq_fma2(w3tp, v3, out2[3]);
+          out2[4] = nq_fma2(w3tp, nq_fma2(make_float2(-(h.x + h.x), -(h.y + h.y)), g2, v4), out2[4]);
         }
       }
+      float out[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) out[c] = out2[c].x + out2[c].y;
       if (quarter != 0) {
 #pragma unroll
         for (int c = 0; c < CH; ++c) outS[((quarter - 1) * ROWS + row) * CH + c] = out[c];
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  asm volatile("bar.sync 2, %0;" ::"n"(TCW + 32) : "memory");   // workers + the issuing warp (the idle warps have left)
+  asm volatile("bar.sync 2, %0;" ::"n"(TCT) : "memory");        // workers + the issuing warps
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 

@@ -60,7 +60,7 @@ int main() {
   long long* d;
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  const Cfg cfgs[] = {{128, 64, 0, 0, 1, 1, 1}, {128, 64, 0, 0, 1, 1, 2}, {128, 64, 0, 0, 1, 1, 4}, {128, 32, 0, 0, 1, 1, 1}, {128, 128, 0, 0, 1, 1, 1},
+  const Cfg cfgs[] = {{128, 64, 0, 0, 1, 1, 1}, {128, 64, 0, 0, 1, 2, 1}, {128, 64, 0, 0, 1, 4, 1}, {128, 128, 0, 0, 1, 2, 1}, {128, 256, 0, 0, 0, 2, 1}, {128, 64, 0, 0, 1, 1, 2}, {128, 64, 0, 0, 1, 1, 4}, {128, 32, 0, 0, 1, 1, 1}, {128, 128, 0, 0, 1, 1, 1},
                       {128, 192, 0, 0, 1, 1, 1}, {128, 256, 0, 0, 1, 1, 1}, {128, 64, 1, 1, 0, 1, 1}, {128, 64, 1, 1, 0, 1, 2}, {64, 16, 1, 0, 0, 1, 1},
                       {64, 16, 1, 0, 0, 1, 4}};
   const int nrep = 512;
