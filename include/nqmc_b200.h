@@ -231,6 +231,13 @@ int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t 
  * The solve is Jacobi-preconditioned CG (S is SPD for reg > 0) run for at most max_iter iterations or until
  * |S x - f| <= tol |f|, entirely in-stream (no host synchronisation). */
 int64_t nqmc_sr_workspace_bytes(int64_t P);
+/* Per-walker log-derivatives, parameter-major: Ot[p * ld + w] = d log|psi(r_w)| / d theta_p, ld >= W.
+ * Replaces: vmap(jax.grad(lambda p: wavefunction(p, r)))(samples) -- src/nqmc/optimizer/vmc.py:120-123 -- in the one
+ * case where the matrix is wanted itself (the O of Stochastic Reconfiguration).  SimpleWavefunction only
+ * (NQMC_ERR_UNSUPPORTED otherwise: the antisymmetric ansatz has 2e4..2e5 parameters, S would be 1.6 .. 160 GB). */
+int nqmc_log_psi_grads(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, nqmc_stream stream);
+/* theta += delta (fp64 update direction from nqmc_sr_update) in the ctx, on the device. */
+int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream stream);
 int nqmc_sr_update(nqmc_ctx* ctx, float* Ot, const float* e_l, int64_t P, int64_t n, int64_t ld, float reg, float lr,
                    int32_t max_iter, double tol, float* S, double* work, double* delta, double* info, nqmc_stream stream);
 

@@ -355,6 +355,10 @@ __global__ void sr_finish_kernel(const int P, const float lr, const double* __re
   }
 }
 
+__global__ void apply_update_kernel(float* __restrict__ theta, const double* __restrict__ delta, const int P) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) theta[i] = (float)((double)theta[i] + delta[i]);
+}
+
 int launch_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                 float alpha, float diag, int symmetric, float* C, int64_t ldc, cudaStream_t st,
                 const double* inv_alpha_dev = nullptr) {
@@ -407,6 +411,26 @@ int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t 
   if (!ctx) return NQMC_ERR_ARG;
   NQMC_CUDA(cudaSetDevice(ctx->device));
   return launch_gram(ctx, A, B, M, N, K, lda, ldb, alpha, diag, symmetric, C, ldc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nqmc_log_psi_grads(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, nqmc_stream stream) {
+  if (!ctx || !r || !Ot || W <= 0 || ld < W) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->sys.kind != NQMC_KIND_SIMPLE) {
+    ctx->err = "nqmc_log_psi_grads: per-walker log-derivatives are materialised for SimpleWavefunction only (the antisymmetric "
+               "ansatz has 2e4..2e5 parameters: its S matrix would not fit; use nqmc_grad_accum)";
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  return nq_simple_grads_per_walker(ctx, r, W, Ot, ld, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream stream) {
+  if (!ctx || !delta || P != ctx->sys.P) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  apply_update_kernel<<<ctx->sm_count, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ctx->theta, delta, (int)P);
+  ctx->theta_dirty = true;
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
 }
 
 int64_t nqmc_sr_workspace_bytes(int64_t P) { return P > 0 ? (int64_t)sizeof(double) * (CG_SCAL + 6 * P + 8) : -1; }

@@ -256,6 +256,7 @@ int nq_simple_logpsi(nqmc_ctx* ctx, const float* r, int64_t W, float* logabs, cu
 int nq_simple_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st);
 int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr_center, const float* e_l,
                     int64_t W, double* out, cudaStream_t st);
+int nq_simple_grads_per_walker(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, cudaStream_t st);
 // Programmatic dependent launch (PDL): a kernel launched through nq_launch_pdl may become resident while its
 // predecessor in the stream is still draining (once every CTA of the predecessor has called nq_pdl_trigger or
 // exited); it must call nq_pdl_wait() before touching anything a predecessor wrote.  Used so that the per-CTA weight

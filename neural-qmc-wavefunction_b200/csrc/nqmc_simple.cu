@@ -194,9 +194,17 @@ __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, co
                                                               const float* __restrict__ r, const float* __restrict__ wgt,
                                                               const double* __restrict__ hdr,
                                                               const float* __restrict__ e_l, const int64_t W,
-                                                              float* __restrict__ part) {
+                                                              float* __restrict__ part, float* __restrict__ Ot,
+                                                              const int64_t ld) {
+  // Ot != nullptr: per-walker mode (Stochastic Reconfiguration): instead of accumulating weight * d log|psi| / d theta,
+  // every walker's log-derivatives are stored parameter-major, Ot[p * ld + w] (the warps of a block own consecutive
+  // walkers, so the 4-byte stores of a parameter fall into one sector per block).
   extern __shared__ __align__(16) float smem[];
   const int HM = simple_hm(s), NH = s.simple.n_hidden, act = s.simple.act, NA = simple_act_floats(s);
+  auto emit = [&](const int idx, const float v, const int64_t w) {
+    if (Ot != nullptr) Ot[(int64_t)idx * ld + w] = v;
+    else atomicAdd(&smem[s.P + idx], v);
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = s.P;
   float* th = smem;
@@ -212,7 +220,8 @@ __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, co
   if (hdr) center = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
   for (int64_t w = (int64_t)blockIdx.x * SW + warp; w < W; w += (int64_t)gridDim.x * SW) {
     float wt = 1.f;
-    if (wgt) wt = wgt[w];
+    if (Ot != nullptr) wt = 1.f;
+    else if (wgt) wt = wgt[w];
     else if (e_l) { float e = e_l[w]; wt = isfinite(e) ? e - center : 0.f; }
     const int D = s.simple.dim[0];
     for (int d = lane; d < D; d += 32) hbuf[d] = r[(int64_t)d * W + w];
@@ -239,10 +248,10 @@ __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, co
       const int K = s.simple.dim[NH];
       const float* Wo = th + s.simple.offW[NH];
       for (int k = lane; k < K; k += 32) {
-        atomicAdd(&acc[s.simple.offW[NH] + k], wt * hbuf[off + k]);
+        emit(s.simple.offW[NH] + k, wt * hbuf[off + k], w);
         dl0[k] = wt * Wo[k] * (NH > 0 ? abuf[off + k] : 1.f);
       }
-      if (lane == 0) atomicAdd(&acc[s.simple.offb[NH]], wt);
+      if (lane == 0) emit(s.simple.offb[NH], wt, w);
       __syncwarp();
     }
     float* dcur = dl0;
@@ -252,10 +261,10 @@ __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, co
       off -= K;
       const float* Wl = th + s.simple.offW[l];
       const float* in = hbuf + off;
-      for (int j = lane; j < M; j += 32) atomicAdd(&acc[s.simple.offb[l] + j], dcur[j]);
+      for (int j = lane; j < M; j += 32) emit(s.simple.offb[l] + j, dcur[j], w);
       for (int k = 0; k < K; ++k) {           // dW[k][j] += in[k] * delta[j]: lanes over j (conflict-free atomics)
         const float hk = in[k];
-        for (int j = lane; j < M; j += 32) atomicAdd(&acc[s.simple.offW[l] + k * M + j], hk * dcur[j]);
+        for (int j = lane; j < M; j += 32) emit(s.simple.offW[l] + k * M + j, hk * dcur[j], w);
       }
       if (l > 0) {
         for (int k = lane; k < K; k += 32) {
@@ -270,7 +279,8 @@ __global__ void __launch_bounds__(SW * 32) simple_grad_kernel(const DevSys s, co
     __syncwarp();
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < P; i += blockDim.x) part[(int64_t)blockIdx.x * P + i] = acc[i];
+  if (Ot == nullptr)
+    for (int i = threadIdx.x; i < P; i += blockDim.x) part[(int64_t)blockIdx.x * P + i] = acc[i];
 }
 
 __global__ void simple_grad_finish_kernel(const float* __restrict__ part, const int nblk, const int P,
@@ -338,9 +348,30 @@ int nq_simple_grads(nqmc_ctx* ctx, const float* r, const float* wgt, const doubl
   if (nblk > cap) nblk = cap;
   if (nblk > 2 * ctx->sm_count) nblk = 2 * ctx->sm_count;
   if (nblk < 1) nblk = 1;
-  simple_grad_kernel<<<(unsigned)nblk, SW * 32, smem, st>>>(s, ctx->theta, r, wgt, hdr_center, e_l, W, ctx->part_mlp);
+  simple_grad_kernel<<<(unsigned)nblk, SW * 32, smem, st>>>(s, ctx->theta, r, wgt, hdr_center, e_l, W, ctx->part_mlp, nullptr, 0);
   NQMC_LAUNCH_CHECK();
   simple_grad_finish_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(ctx->part_mlp, (int)nblk, s.P, out);
+  NQMC_LAUNCH_CHECK();
+  return NQMC_OK;
+}
+
+// per-walker log-derivatives, parameter-major: Ot[p * ld + w] = d log|psi(r_w)| / d theta_p   (SimpleWavefunction)
+int nq_simple_grads_per_walker(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, cudaStream_t st) {
+  const DevSys& s = ctx->sys;
+  const size_t smem = simple_grad_smem(s);
+  if (smem > 227 * 1024) {
+    ctx->err = "SimpleWavefunction gradient: parameter block does not fit in shared memory";
+    return NQMC_ERR_UNSUPPORTED;
+  }
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    NQMC_CUDA(cudaFuncSetAttribute(simple_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int64_t nblk = (W + SW - 1) / SW;
+  if (nblk > 4 * ctx->sm_count) nblk = 4 * ctx->sm_count;
+  simple_grad_kernel<<<(unsigned)nblk, SW * 32, smem, st>>>(s, ctx->theta, r, nullptr, nullptr, nullptr, W, nullptr, Ot, ld);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }

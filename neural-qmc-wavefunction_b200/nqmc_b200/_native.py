@@ -32,7 +32,7 @@ EXPORTS = [
     "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
     "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync",
-    "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update",
+    "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update", "nqmc_log_psi_grads", "nqmc_apply_update",
 ]
 
 
@@ -109,6 +109,8 @@ def load_library():
     lib.nqmc_sr_workspace_bytes.argtypes = [i64]
     lib.nqmc_sr_workspace_bytes.restype = i64
     lib.nqmc_sr_update.argtypes = [vp, vp, vp, i64, i64, i64, f32, f32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
+    lib.nqmc_log_psi_grads.argtypes = [vp, vp, i64, vp, i64, vp]
+    lib.nqmc_apply_update.argtypes = [vp, vp, i64, vp]
     lib.nqmc_device_count.argtypes = []
     lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
     lib.nqmc_dev_free.argtypes = [C.c_int, vp]
@@ -617,6 +619,20 @@ class Context:
         self._check(self.lib.nqmc_gram(self.h, _ptr(A), _ptr(Bm), M, N, K, K, K, float(alpha), float(diag), int(sym),
                                        out.ptr, N, self.stream), "nqmc_gram")
         return out
+
+    def log_psi_grads(self, r_soa) -> DeviceArray:
+        """Per-walker log-derivatives, parameter-major [P][W] (nqmc_log_psi_grads; SimpleWavefunction only)."""
+        W = _shape(r_soa)[1]
+        if W % 4:
+            raise ValueError("log_psi_grads: the walker count must be a multiple of 4 (TMA row pitch of the SR kernels)")
+        self.reserve(W)
+        Ot = self.empty((self.P, W))
+        self._check(self.lib.nqmc_log_psi_grads(self.h, _ptr(r_soa), W, Ot.ptr, W, self.stream), "nqmc_log_psi_grads")
+        return Ot
+
+    def apply_update(self, delta) -> None:
+        """theta += delta (device fp64 vector) in place in the context."""
+        self._check(self.lib.nqmc_apply_update(self.h, _ptr(delta), self.P, self.stream), "nqmc_apply_update")
 
     def sr_update(self, Ot, e_l, reg: float, lr: float, max_iter: int = 200, tol: float = 1e-6):
         """One Stochastic Reconfiguration update (nqmc_sr_update).  Ot: device [P][n] (centred in place), e_l: device [n].

@@ -123,6 +123,12 @@ class VMCOptimizer:
     device_update: bool = False     # extension: fused clip + Adam on the GPU, theta stays resident
     adaptive_step: bool = False     # extension: adapt step_size toward target_acceptance in burn-in
     target_acceptance: float = 0.5
+    optimizer: str = "adam"         # "adam" (the reference's optax chain) or "sr": Stochastic Reconfiguration on the device
+                                    # ([SPEC] .github/phase6-issue-body.md:130-182; nqmc_log_psi_grads + nqmc_sr_update),
+                                    # SimpleWavefunction, single GPU; learning_rate is the SR step, clip_grad is unused
+    sr_regularization: float = 1e-3
+    sr_max_iter: int = 300
+    sr_tol: float = 1e-6
     n_blocks: int = 0               # extension: > 0 adds metrics["energy_std_blocked"], the error
                                     # bar from n_blocks blocks per chain (autocorrelation-aware; analysis.chain_blocking)
 
@@ -168,7 +174,10 @@ class VMCOptimizer:
         n_burn = self.n_burn if state.step == 0 else 10                      # vmc.py:247
         W = hi - lo
         blocked = None
-        if self.n_samples == 1 and normals is None and uniforms is None:
+        if self.optimizer not in ("adam", "sr"):
+            raise ValueError(f"unknown optimizer {self.optimizer!r}")
+        sr_delta = None
+        if self.n_samples == 1 and normals is None and uniforms is None and self.optimizer == "adam":
             # burn-in, then the library's fused walker step: sampled move + E_L + header + centred reverse pass
             _, sstate, _, _ = sampler.sample_device(key, log_prob_fn, state.sampler_state, 0, n_burn, 1, walker_id0=lo,
                                                     donate=True, want_rate=False)
@@ -199,6 +208,12 @@ class VMCOptimizer:
             parallel.reduce_over_ranks_(ctx, gsum)
             h = hdr.numpy(ctx.stream)
             rank, ws = parallel.world()
+            if self.optimizer == "sr":
+                if ws > 1:
+                    raise NotImplementedError("optimizer='sr' is single-GPU (S is not reduced over ranks)")
+                Ot = ctx.log_psi_grads(samples)                               # phase6-issue-body.md:152-165 (O, parameter-major)
+                sr_delta, sr_info, _ = ctx.sr_update(Ot, e, self.sr_regularization, self.learning_rate, self.sr_max_iter,
+                                                     self.sr_tol)            # :168-181
             if self.n_blocks > 0 and self.n_samples >= self.n_blocks:
                 b3 = ctx.blocked_stats(e, self.n_samples, W, self.n_blocks)
                 if ws > 1:
@@ -209,7 +224,13 @@ class VMCOptimizer:
                 a = parallel.group().all_reduce_sum(np.array([acc * W, float(W)]))
                 acc = float(a[0] / a[1])
         mean, std, n_bad = _stats(h)
-        if self.device_update:
+        if sr_delta is not None:
+            ctx.apply_update(sr_delta)                                        # theta += -lr S^-1 f, on the device
+            new_params = unravel(ctx.get_params(), params)
+            opt_state = dict(state.opt_state, count=int(state.opt_state["count"]) + 1)
+            info = sr_info.numpy(ctx.stream)
+            grad_norm = float(info[3])                                        # |f| = |2 <(E - <E>) O>|, the same quantity as vmc.py:264-266
+        elif self.device_update:
             opt = state.opt_state
             mu = opt["mu"] if isinstance(opt["mu"], DeviceArray) else ctx.upload(np.asarray(opt["mu"], np.float32))
             nu = opt["nu"] if isinstance(opt["nu"], DeviceArray) else ctx.upload(np.asarray(opt["nu"], np.float32))
@@ -227,6 +248,8 @@ class VMCOptimizer:
         new_state = VMCState(new_params, opt_state, sampler_state, state.step + 1)
         metrics = {"energy": float(mean), "energy_std": float(std), "acceptance_rate": float(acc),
                    "grad_norm": grad_norm, "n_bad": float(n_bad)}
+        if sr_delta is not None:
+            metrics["sr_cg_iterations"], metrics["sr_residual"] = float(info[0]), float(info[1])
         if self.adaptive_step:
             metrics["step_size"] = float(sampler.step_size)
         if blocked is not None:
