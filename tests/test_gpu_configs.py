@@ -33,6 +33,7 @@ def _setup(n_atoms, hidden, W, cusp=False, bf=False, seed=0):
 
 
 @pytest.mark.parametrize("name,n_atoms,hidden,W,cusp,bf", [
+    ("H4-65536", 4, 64, 65536, False, False),               # the benchmarked configuration on the benchmarked (tcgen05) path
     ("H6-bf-cusp-32768", 6, 128, 32768, True, True),
     ("H10-131072", 10, 128, 131072, False, False),
 ])
@@ -91,6 +92,16 @@ def test_full_size_properties(name, n_atoms, hidden, W, cusp, bf):
     e_ref, _, sg_ref, la_ref = o.local_energy(theta.astype(np.float64), r_aos)
     assert np.median(rel_err(e[idx], e_ref)) <= 1e-4
     assert np.median(rel_err(la_c[idx], la_ref)) <= 1e-5
+    # (7) reverse pass at full launch size against the oracle: weights that are non-zero on the subset only
+    if not bf:
+        wsub = np.zeros(W, dtype=np.float32)
+        wsub[idx] = rng.standard_normal(idx.size).astype(np.float32)
+        gsub = ctx.grad_accum(soa, torch.as_tensor(wsub).to(dev)).cpu().numpy()
+        O = o.grad_log_psi(theta.astype(np.float64), r_aos)
+        ref = (wsub[idx].astype(np.float64)[:, None] * O).sum(0)
+        scale = (np.abs(wsub[idx]).astype(np.float64)[:, None] * np.abs(O)).sum(0)
+        err = np.abs(gsub - ref) / np.maximum(scale, 1e-3)
+        assert np.median(err) <= 1e-5 and np.quantile(err, 0.99) <= 1e-3, (np.median(err), np.quantile(err, 0.99))
 
 
 def test_h4_dissociation_sweep_16_geometries():
