@@ -163,6 +163,41 @@ def vmc_iteration_rate(W, iters=20):
             "last_metrics": m, "timing": "host wall clock around VMCOptimizer.step (it synchronises to return its metrics)"}
 
 
+def sr_syrk_rate(ctx, peak3):
+    """S = O^T O / n + reg I for P parameters x n samples on the tcgen05 3xTF32 SYRK (nqmc_gram, TMA-fed),
+    device time by CUDA events.  P = 4,673 is config 1's SimpleWavefunction (64, 64); 19,976 the H4 ansatz of the headline."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    out = []
+    for P, n in ((4673, 65536), (19976, 16384)):
+        g = torch.Generator(device=dev).manual_seed(1)
+        Ot = torch.randn((P, n), device=dev, dtype=torch.float32, generator=g)
+        S = torch.empty((P, P), device=dev, dtype=torch.float32)
+        torch.cuda.synchronize()
+
+        def run():
+            rc = ctx.lib.nqmc_gram(ctx.h, Ot.data_ptr(), Ot.data_ptr(), P, P, n, n, n, 1.0 / n, 1e-3, 1, S.data_ptr(), P, ctx.stream)
+            assert rc == 0, rc
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        tiles = sum(1 for tm in range((P + 127) // 128) for tn in range((P + 255) // 256) if tn * 256 + 256 > tm * 128)
+        alg, exe = n * P * (P + 1.0), tiles * 128 * 256 * 2.0 * n
+        out.append({"P": P, "n_samples": n, "ms": ms, "algorithmic_tflops": alg / ms / 1e9, "executed_tflops": exe / ms / 1e9,
+                    "frac_of_tf32_over_3_executed": exe / ms / 1e9 / peak3, "frac_of_tf32_over_3_algorithmic": alg / ms / 1e9 / peak3})
+        del Ot, S
+        torch.cuda.empty_cache()
+    return {"kernel": "gram_kernel (nqmc_gram.cu): TMA SWIZZLE_128B -> smem ring -> tf32 hi/lo split -> tcgen05.mma M128 N256 K8, "
+                      "upper-triangle tiles only, fp32 flush every 256 samples", "cases": out,
+            "note": "algorithmic = n P (P+1) flops (upper triangle); executed = tiles touching it"}
+
+
 def other_configs(flush, peak3, ffma_peak):
     """The BASELINE configs that are not the headline, on ONE GPU at their per-GPU sizes (configs[2] and [4] name 8
     GPUs: 262,144 / 8 and 1,048,576 / 8 walkers), same event timing and L2 flush as the headline."""
@@ -175,8 +210,10 @@ def other_configs(flush, peak3, ffma_peak):
             d = time_fused_step(*args_, steps=5, warm=2, flush=flush)
             d["frac_of_tf32_over_3"] = d["achieved_tflops"] / peak3
             d["frac_of_ffma_peak"] = d["achieved_tflops"] / ffma_peak
-            d["kernels"] = ("tcgen05 3xTF32: value + 5-channel forward (nqmc_orbital_fwd_pc.cu); FP32 FFMA: reverse pass"
-                            + (", 10-channel backflow forward" if args_[4] else ""))
+            d["kernels"] = ("tcgen05 3xTF32: value + 5-channel forward (nqmc_orbital_fwd_pc.cu; backflow: G-weighted Laplacian "
+                            "channel) and the reverse pass (nqmc_orbital_bwd128.cu: value sweep, D1 kernel, TMA-fed "
+                            "weight-gradient Gram kernel)"
+                            + ("; FP32: backflow / cusp per-walker kernels" if args_[4] else ""))
             out[name] = d
         except Exception as e:      # report, do not hide
             out[name] = {"error": repr(e)}
@@ -458,6 +495,10 @@ def run_ours(args):
             out["sustained"] = sustained_run(ctx, one_step, Wl, flops_step, local, peak3, tf32_rec)
             out["vmc_iteration"] = vmc_iteration_rate(Wl)
             out["other_configs"] = other_configs(flush, peak3, ffma_peak)
+            try:
+                out["sr_syrk"] = sr_syrk_rate(ctx, peak3)
+            except Exception as e:      # report, do not hide
+                out["sr_syrk"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_walkers, steps=2, warmup=1)
     if world > 1:

@@ -12,3 +12,11 @@ for K in $(echo "$KRE" | tr '|' ' '); do
   ncu --set full --clock-control none --import-source on -k regex:"$K" -s 3 -c 1 -o gpurun_out/${TAG}_prof_$K $CMD > gpurun_out/${TAG}_ncu_full_$K.log 2>&1
 done
 ls -la gpurun_out | tail -8
+# the TMA-fed kernels: SR SYRK (scripts/time_sr.py) and the 128-wide reverse pass (scripts/exp/launches_h128.py)
+python scripts/time_sr.py > gpurun_out/${TAG}_sr_timing.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 1 -c 1 -o gpurun_out/${TAG}_prof_gram python scripts/time_sr.py > gpurun_out/${TAG}_ncu_full_gram.log 2>&1
+python scripts/exp/launches_h128.py > /dev/null 2>&1 &&
+for K in bwd128_d1_kernel bwd128_gram_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:"$K" -s 3 -c 1 -o gpurun_out/${TAG}_prof_$K python scripts/exp/launches_h128.py > gpurun_out/${TAG}_ncu_full_$K.log 2>&1
+done
+ls -la gpurun_out | grep ${TAG}

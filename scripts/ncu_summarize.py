@@ -19,13 +19,15 @@ for r in data:
     a = agg.setdefault(r[ki].split("(")[0][:90], [0, 0.0])
     a[0] += 1
     a[1] += v
-tot = sum(a[1] for a in agg.values())
+own = lambda k: not any(t in k for t in ('cutlass', 'ffma_peak', 'at::', 'cublas'))   # the bench also measures its roofline denominators
+tot = sum(a[1] for k, a in agg.items() if own(k))
 with open(f"profiles/{tag}_launches_summary.txt", "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 3 --burn 3 --no-cpu-baseline)\n")
-    f.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
+    f.write("# per-launch times are cold-cache and serialised: compare SHARES (share = of this repository's kernels; the cuBLAS / FFMA peak probes are marked)\n")
     f.write(f"{'total_us':>12} {'launches':>8} {'us/launch':>10} {'share':>7}  kernel\n")
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
-        f.write(f"{t:12.1f} {n:8d} {t / n:10.1f} {100 * t / tot:6.1f}%  {k}\n")
+        share = f"{100 * t / tot:6.1f}%" if own(k) else "  (peak)"
+        f.write(f"{t:12.1f} {n:8d} {t / n:10.1f} {share}  {k}\n")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 hdr, units, body = rr[0], rr[1], rr[2:]
