@@ -239,7 +239,7 @@ def other_configs(flush, peak3, ffma_peak):
             "walkers_per_gpu": tot, "ms_per_step": ms, "value_per_gpu": tot / (ms * 1e-3), "unit": "walker-steps/s",
             "achieved_tflops": fl * tot / (ms * 1e-3) / 1e12, "frac_of_tf32_over_3": fl * tot / (ms * 1e-3) / 1e12 / peak3,
             "energies": [round(o["energy"], 4) for o in sw.results()][:4],
-            "kernels": "all three orbital kernels tcgen05 3xTF32; 16 contexts x 9 launches back to back on one stream"}
+            "kernels": "all three orbital kernels tcgen05 3xTF32; 16 contexts x 9 launches dealt over 8 streams that fork from / join the timed stream"}
     except Exception as e:
         out["configs[3] sweep"] = {"error": repr(e)}
     return out

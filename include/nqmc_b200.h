@@ -305,6 +305,9 @@ int nqmc_dev_copy_rows(int device, void* dst, size_t dst_pitch, const void* src,
 int nqmc_dev_memset(int device, void* dst, int value, size_t bytes, nqmc_stream stream);
 int nqmc_stream_create(int device, nqmc_stream* out);
 int nqmc_stream_destroy(int device, nqmc_stream stream);
+/* Work enqueued on `waiter` after this call starts only after everything enqueued on `signal` before it has finished
+ * (event record + stream wait; fork / join of independent contexts that run on their own streams). */
+int nqmc_stream_wait(int device, nqmc_stream waiter, nqmc_stream signal);
 int nqmc_stream_sync(int device, nqmc_stream stream);
 const char* nqmc_mem_last_error(void);
 

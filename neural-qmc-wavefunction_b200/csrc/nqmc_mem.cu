@@ -93,6 +93,16 @@ int nqmc_stream_create(int device, nqmc_stream* out) {
   return NQMC_OK;
 }
 
+int nqmc_stream_wait(int device, nqmc_stream waiter, nqmc_stream signal) {
+  MEM_CUDA(cudaSetDevice(device));
+  cudaEvent_t ev;
+  MEM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  MEM_CUDA(cudaEventRecord(ev, reinterpret_cast<cudaStream_t>(signal)));
+  MEM_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(waiter), ev, 0));
+  MEM_CUDA(cudaEventDestroy(ev));            // released once the wait has been satisfied
+  return NQMC_OK;
+}
+
 int nqmc_stream_destroy(int device, nqmc_stream st) {
   if (!st) return NQMC_OK;
   MEM_CUDA(cudaSetDevice(device));

@@ -31,7 +31,7 @@ EXPORTS = [
     "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
     "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
-    "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync",
+    "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync", "nqmc_stream_wait",
     "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update", "nqmc_log_psi_grads", "nqmc_apply_update",
 ]
 
@@ -121,6 +121,7 @@ def load_library():
     lib.nqmc_dev_memset.argtypes = [C.c_int, vp, C.c_int, sz, vp]
     lib.nqmc_stream_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.nqmc_stream_destroy.argtypes = [C.c_int, vp]
+    lib.nqmc_stream_wait.argtypes = [C.c_int, vp, vp]
     lib.nqmc_stream_sync.argtypes = [C.c_int, vp]
     lib.nqmc_mem_last_error.argtypes = []
     lib.nqmc_mem_last_error.restype = C.c_char_p

@@ -111,8 +111,10 @@ def test_h4_dissociation_sweep_16_geometries():
     sw = GeometrySweep(bond_lengths=bonds, walkers_per_geometry=16384, hidden=(64, 64), step_size=0.5, seed=3)
     assert len(sw.states) == 16
     sw.burn_in(10)
-    before = [(st.r.clone(), st.logp.clone()) for st in sw.states]
+    sw.synchronize()
+    before = [(st.r.clone(st.ctx.stream), st.logp.clone(st.ctx.stream)) for st in sw.states]   # each geometry runs on its own stream
     sw.step()
+    sw.synchronize()
     res = sw.results()
     for g, (st, out) in enumerate(zip(sw.states, res)):
         assert out["bond_length"] == pytest.approx(bonds[g])
@@ -125,6 +127,7 @@ def test_h4_dissociation_sweep_16_geometries():
             r2, lp2 = before[g]
             e2, h2, g2 = ctx.empty(sw.W), ctx.empty(8, np.float64), ctx.empty(ctx.P, np.float64)
             ctx.walker_step(r2, lp2, sw.step_size, e2, h2, g2, seed=sw.seed + 1000 * g, step=(1 << 20) + sw.t)
+            ctx.synchronize()
             assert np.array_equal(e2.cpu().numpy(), st.e_l.cpu().numpy())
             assert np.array_equal(r2.cpu().numpy(), st.r.cpu().numpy())
             assert np.array_equal(h2.cpu().numpy(), st.hdr.cpu().numpy())
