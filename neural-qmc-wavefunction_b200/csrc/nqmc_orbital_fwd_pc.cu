@@ -319,8 +319,9 @@ __global__ void __launch_bounds__(TCT, 1)
         }
       }
       float out[CH];
+      float2 out2[CH];                                         // even / odd columns of this thread, added at the end
 #pragma unroll
-      for (int c = 0; c < CH; ++c) out[c] = 0.f;
+      for (int c = 0; c < CH; ++c) out2[c] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass, ++ep) {
 #pragma unroll 2
@@ -329,28 +330,27 @@ __global__ void __launch_bounds__(TCT, 1)
           constexpr int CM = CH == 1 ? 1 : 5;                  // channels computed (CH = 4 exists for timing experiments only)
           float acc[CM][UPT];
           {
-            const float2 bv = *reinterpret_cast<const float2*>(b1s + j0);
-            acc[0][0] = bv.x; acc[0][1] = bv.y;
-#pragma unroll
-            for (int c = 1; c < CM; ++c) acc[c][0] = acc[c][1] = 0.f;
-            float ew[UPT] = {0.f, 0.f};                            // sum_a e_a we_a : part of the value and of the Laplacian
-            float ewq[UPT] = {0.f, 0.f};                           // GW: sum_a q_a e_a we_a (Laplacian channel)
-            const float pc[3] = {x, y, z};
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float2 wv = *reinterpret_cast<const float2*>(W1s + d * H + j0);
-              acc[0][0] = fmaf(pc[d], wv.x, acc[0][0]);
-              acc[0][1] = fmaf(pc[d], wv.y, acc[0][1]);
+            // the thread's two hidden units are one packed pair: every FMA / MUL / ADD below is one FFMA2 / FMUL2 / FADD2
+            float2 pa[CM];
+            pa[0] = *reinterpret_cast<const float2*>(b1s + j0);
+            float2 ew = make_float2(0.f, 0.f);                     // sum_a e_a we_a : part of the value and of the Laplacian
+            float2 ewq = make_float2(0.f, 0.f);                    // GW: sum_a q_a e_a we_a (Laplacian channel)
+            {
+              const float2 w0 = *reinterpret_cast<const float2*>(W1s + 0 * H + j0);
+              const float2 w1 = *reinterpret_cast<const float2*>(W1s + 1 * H + j0);
+              const float2 w2 = *reinterpret_cast<const float2*>(W1s + 2 * H + j0);
+              pa[0] = nq_fma2(nq_bc2(x), w0, pa[0]);
+              pa[0] = nq_fma2(nq_bc2(y), w1, pa[0]);
+              pa[0] = nq_fma2(nq_bc2(z), w2, pa[0]);
               if constexpr (CM == 5) {
-                acc[1 + d][0] += wv.x;
-                acc[1 + d][1] += wv.y;
+                pa[1] = w0; pa[2] = w1; pa[3] = w2;
+                pa[4] = make_float2(0.f, 0.f);
               }
             }
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
               const float2 wd = *reinterpret_cast<const float2*>(W1s + (3 + a) * H + j0);
               const float2 we = *reinterpret_cast<const float2*>(W1s + (3 + NA + a) * H + j0);
-              const float wdv[UPT] = {wd.x, wd.y}, wev[UPT] = {we.x, we.y};
               float dd, ex, ux = 0.f, uy = 0.f, uz = 0.f, ti = 0.f, qa = 1.f;
               if constexpr (C::FEAT_SMEM) {
                 const float4 fa = featA[a * ROWS + row];
@@ -363,33 +363,33 @@ __global__ void __launch_bounds__(TCT, 1)
                 dd = fdd[a]; ex = fex[a]; ux = fux[a]; uy = fuy[a]; uz = fuz[a]; ti = fti[a];
                 if constexpr (GW) qa = fq[a];
               }
-#pragma unroll
-              for (int u2 = 0; u2 < UPT; ++u2) {
-                const float ewe = ex * wev[u2];
-                ew[u2] += ewe;
-                if constexpr (GW) ewq[u2] = fmaf(qa, ewe, ewq[u2]);
-                acc[0][u2] = fmaf(dd, wdv[u2], acc[0][u2]);
-                if constexpr (CM == 5) {
-                  const float sv = fmaf(-ex, wev[u2], wdv[u2]);
-                  acc[1][u2] = fmaf(ux, sv, acc[1][u2]);
-                  acc[2][u2] = fmaf(uy, sv, acc[2][u2]);
-                  acc[3][u2] = fmaf(uz, sv, acc[3][u2]);
-                  acc[4][u2] = fmaf(ti, sv, acc[4][u2]);
-                }
-              }
-            }
-#pragma unroll
-            for (int u2 = 0; u2 < UPT; ++u2) {   // tanh rules: lap' = tp (lap - 2 h |grad|^2)
-              const float h = nq_tanh(acc[0][u2] + ew[u2]);
+              const float2 ewe = nq_mul2(nq_bc2(ex), we);
+              ew = nq_add2(ew, ewe);
+              if constexpr (GW) ewq = nq_fma2(nq_bc2(qa), ewe, ewq);
+              pa[0] = nq_fma2(nq_bc2(dd), wd, pa[0]);
               if constexpr (CM == 5) {
-                const float tp = fmaf(-h, h, 1.0f);
-                const float g2 = GW ? quad(acc[1][u2], acc[2][u2], acc[3][u2])
-                                    : fmaf(acc[1][u2], acc[1][u2], fmaf(acc[2][u2], acc[2][u2], acc[3][u2] * acc[3][u2]));
-                acc[4][u2] = tp * fmaf(-(h + h), g2, acc[4][u2] + (GW ? ewq[u2] : ew[u2]));
-                acc[1][u2] *= tp; acc[2][u2] *= tp; acc[3][u2] *= tp;
+                const float2 sv = nq_fma2(nq_bc2(-ex), we, wd);
+                pa[1] = nq_fma2(nq_bc2(ux), sv, pa[1]);
+                pa[2] = nq_fma2(nq_bc2(uy), sv, pa[2]);
+                pa[3] = nq_fma2(nq_bc2(uz), sv, pa[3]);
+                pa[4] = nq_fma2(nq_bc2(ti), sv, pa[4]);
               }
-              acc[0][u2] = h;
             }
+            // tanh rules: lap' = tp (lap - 2 h |grad|^2)
+            const float2 h = nq_tanh2(nq_add2(pa[0], ew));
+            if constexpr (CM == 5) {
+              const float2 tp = nq_fma2(make_float2(-h.x, -h.y), h, nq_bc2(1.0f));
+              float2 g2;
+              if constexpr (GW) g2 = make_float2(quad(pa[1].x, pa[2].x, pa[3].x), quad(pa[1].y, pa[2].y, pa[3].y));
+              else g2 = nq_fma2(pa[1], pa[1], nq_fma2(pa[2], pa[2], nq_mul2(pa[3], pa[3])));
+              pa[4] = nq_mul2(tp, nq_fma2(make_float2(-(h.x + h.x), -(h.y + h.y)), g2, nq_add2(pa[4], GW ? ewq : ew)));
+              pa[1] = nq_mul2(pa[1], tp);
+              pa[2] = nq_mul2(pa[2], tp);
+              pa[3] = nq_mul2(pa[3], tp);
+            }
+            pa[0] = h;
+#pragma unroll
+            for (int c = 0; c < CM; ++c) { acc[c][0] = pa[c].x; acc[c][1] = pa[c].y; }
           }
           if constexpr (BW) {
             float* hr = bw.hT + ((int64_t)m * H + j0) * bw.rows_pad + rid;
@@ -429,28 +429,37 @@ __global__ void __launch_bounds__(TCT, 1)
           }
           const int jb = pass * NT + c0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float h = nq_tanh(v[0][j] + b2s[jb + j]);
-            const float w3 = W3s[jb + j];
+          for (int j = 0; j < 8; j += 2) {                      // two columns per packed instruction
+            const float2 h = nq_tanh2(nq_add2(make_float2(v[0][j], v[0][j + 1]), *reinterpret_cast<const float2*>(b2s + jb + j)));
+            const float2 w3 = *reinterpret_cast<const float2*>(W3s + jb + j);
+            const float2 tp = nq_fma2(make_float2(-h.x, -h.y), h, nq_bc2(1.0f));
             if constexpr (BW) {
-              gW3[8 * sub + j] = fmaf(seed, h, gW3[8 * sub + j]);
-              bw.dT[((int64_t)m * H + jb + j) * bw.rows_pad + rid] = seed * w3 * fmaf(-h, h, 1.0f);
+              const float2 gw = nq_fma2(nq_bc2(seed), h, make_float2(gW3[8 * sub + j], gW3[8 * sub + j + 1]));
+              gW3[8 * sub + j] = gw.x; gW3[8 * sub + j + 1] = gw.y;
+              const float2 d2 = nq_mul2(nq_mul2(nq_bc2(seed), w3), tp);
+              float* dst = bw.dT + ((int64_t)m * H + jb + j) * bw.rows_pad + rid;
+              dst[0] = d2.x;
+              dst[bw.rows_pad] = d2.y;
               continue;
             }
-            out[0] = fmaf(w3, h, out[0]);
+            out2[0] = nq_fma2(w3, h, out2[0]);
             if constexpr (CH >= 4) {
-              const float tp = fmaf(-h, h, 1.0f);
-              const float g2 = GW ? quad(v[1][j], v[2][j], v[3][j])
-                                  : fmaf(v[1][j], v[1][j], fmaf(v[2][j], v[2][j], v[3][j] * v[3][j]));
-              const float w3tp = w3 * tp;
-              out[1] = fmaf(w3tp, v[1][j], out[1]);
-              out[2] = fmaf(w3tp, v[2][j], out[2]);
-              out[3] = fmaf(w3tp, v[3][j], out[3]);
-              out[CH - 1] = fmaf(w3tp, fmaf(-(h + h), g2, v[CH - 1][j]), out[CH - 1]);
+              const float2 v1 = make_float2(v[1][j], v[1][j + 1]), v2 = make_float2(v[2][j], v[2][j + 1]);
+              const float2 v3 = make_float2(v[3][j], v[3][j + 1]), vl = make_float2(v[CH - 1][j], v[CH - 1][j + 1]);
+              float2 g2;
+              if constexpr (GW) g2 = make_float2(quad(v1.x, v2.x, v3.x), quad(v1.y, v2.y, v3.y));
+              else g2 = nq_fma2(v1, v1, nq_fma2(v2, v2, nq_mul2(v3, v3)));
+              const float2 w3tp = nq_mul2(w3, tp);
+              out2[1] = nq_fma2(w3tp, v1, out2[1]);
+              out2[2] = nq_fma2(w3tp, v2, out2[2]);
+              out2[3] = nq_fma2(w3tp, v3, out2[3]);
+              out2[CH - 1] = nq_fma2(w3tp, nq_fma2(make_float2(-(h.x + h.x), -(h.y + h.y)), g2, vl), out2[CH - 1]);
             }
           }
         }
       }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) out[c] = out2[c].x + out2[c].y;
       if constexpr (BW) {
         if (quarter == 0) gb3 += seed;
         continue;
