@@ -408,8 +408,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step((1 << 22) + i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = time.perf_counter() - t0                           # this rank's own finish (every step ends synchronised);
+    barrier()                                                  # the max over ranks is taken below
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
