@@ -109,6 +109,7 @@ void nq_comm_free(nqmc_ctx* ctx) {
   ctx->comm = nullptr;
 }
 
+int nq_comm_rank(const nqmc_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 bool nq_comm_active(const nqmc_ctx* ctx) { return ctx->comm && ctx->comm->attached && ctx->comm->world > 1; }
 
 int nq_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out) {

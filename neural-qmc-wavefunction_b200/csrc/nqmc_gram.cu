@@ -211,14 +211,11 @@ __global__ void sr_energy_mean_kernel(const float* __restrict__ e_l, const int64
     atomicAdd(&sums[1], a);
   }
 }
-// one CTA per parameter row p: mean over the finite-energy samples, centre the row in place (samples with a
-// non-finite energy become 0 and drop out of S and f), f[p] = 2/n sum_w (E_w - Ebar) Oc[p][w]
-__global__ void __launch_bounds__(256) sr_center_kernel(float* __restrict__ Ot, const float* __restrict__ e_l, const int64_t n,
-                                                        const int64_t ld, const double* __restrict__ sums, double* __restrict__ f) {
+// one CTA per parameter row p: rs[p] = sum over the finite-energy samples of Ot[p][w]
+__global__ void __launch_bounds__(256) sr_rowsum_kernel(const float* __restrict__ Ot, const float* __restrict__ e_l, const int64_t n,
+                                                        const int64_t ld, double* __restrict__ rs) {
   __shared__ double red[8];
-  __shared__ double mean_s;
-  float* row = Ot + (int64_t)blockIdx.x * ld;
-  const double nf = fmax(sums[0], 1.0), ebar = sums[1] / nf;
+  const float* row = Ot + (int64_t)blockIdx.x * ld;
   double a = 0.0;
   for (int64_t w = threadIdx.x; w < n; w += 256)
     if (isfinite(e_l[w])) a += (double)row[w];
@@ -228,10 +225,18 @@ __global__ void __launch_bounds__(256) sr_center_kernel(float* __restrict__ Ot, 
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < 8; ++i) t += red[i];
-    mean_s = t / nf;
+    rs[blockIdx.x] = t;
   }
-  __syncthreads();
-  const float mean = (float)mean_s;
+}
+// centre row p in place with the (global) mean rs[p] / n_finite; samples with a non-finite energy become 0 and drop out
+// of S and f; f[p] = 2 / n_finite * sum_w (E_w - Ebar) Oc[p][w]   (this rank's part of it)
+__global__ void __launch_bounds__(256) sr_center_kernel(float* __restrict__ Ot, const float* __restrict__ e_l, const int64_t n,
+                                                        const int64_t ld, const double* __restrict__ sums,
+                                                        const double* __restrict__ rs, double* __restrict__ f) {
+  __shared__ double red[8];
+  float* row = Ot + (int64_t)blockIdx.x * ld;
+  const double nf = fmax(sums[0], 1.0), ebar = sums[1] / nf;
+  const float mean = (float)(rs[blockIdx.x] / nf);
   double g = 0.0;
   for (int64_t w = threadIdx.x; w < n; w += 256) {
     const float e = e_l[w];
@@ -243,7 +248,6 @@ __global__ void __launch_bounds__(256) sr_center_kernel(float* __restrict__ Ot, 
     row[w] = o;
   }
   g = warp_sum(g);
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = g;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -256,12 +260,33 @@ __global__ void __launch_bounds__(256) sr_center_kernel(float* __restrict__ Ot, 
 // CG state in `ws` (doubles): [0] rz, [1] pq, [2] rz_new, [3] bb (= f.f), [4] converged flag, [5] iterations done,
 // [6] rr (unpreconditioned residual norm^2); vectors x, r, p, q, dinv follow (P each).
 constexpr int CG_SCAL = 8;
-__global__ void cg_init_kernel(const float* __restrict__ S, const int64_t lds, const double* __restrict__ f, const int P,
-                               double* __restrict__ ws) {
+// Deterministic block sum (fixed shuffle / shared-memory order): the CG scalars must come out bit-identical on every rank
+// of a multi-GPU run (all ranks then take identical steps), so these kernels run as ONE block of 1024 threads instead of
+// accumulating with atomics.  P <= ~2e4: a handful of elements per thread.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32) {
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+// d[i] = S[i][i] (this rank's part of the diagonal; summed over ranks before cg_init_kernel)
+__global__ void cg_diag_kernel(const float* __restrict__ S, const int64_t lds, const int P, double* __restrict__ ws) {
+  double* dinv = ws + CG_SCAL + 4 * (int64_t)P;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) dinv[i] = (double)S[(int64_t)i * lds + i];
+}
+__global__ void __launch_bounds__(1024) cg_init_kernel(const double* __restrict__ f, const int P, double* __restrict__ ws) {
+  __shared__ double red[32];
   double* x = ws + CG_SCAL; double* r = x + P; double* p = r + P; double* dinv = p + 2 * (int64_t)P;
   double rz = 0.0, bb = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-    const double d = (double)S[(int64_t)i * lds + i];
+    const double d = dinv[i];
     const double di = d > 0.0 ? 1.0 / d : 1.0;
     dinv[i] = di;
     x[i] = 0.0;
@@ -270,15 +295,15 @@ __global__ void cg_init_kernel(const float* __restrict__ S, const int64_t lds, c
     rz += f[i] * di * f[i];
     bb += f[i] * f[i];
   }
-  rz = warp_sum(rz);
-  bb = warp_sum(bb);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&ws[0], rz);
-    atomicAdd(&ws[3], bb);
-    atomicAdd(&ws[6], bb);
+  rz = block_sum(rz, red);
+  bb = block_sum(bb, red);
+  if (threadIdx.x == 0) {
+    ws[0] = rz;
+    ws[3] = bb;
+    ws[6] = bb;
   }
 }
-// q = S p (one warp per row), pq += p.q
+// q = S p (one warp per row; with several ranks this rank's part of it, summed over ranks before cg_dot_kernel)
 __global__ void __launch_bounds__(256) cg_matvec_kernel(const float* __restrict__ S, const int64_t lds, const int P, double* __restrict__ ws) {
   if (ws[4] != 0.0) return;
   const double* p = ws + CG_SCAL + 2 * (int64_t)P;
@@ -294,13 +319,22 @@ __global__ void __launch_bounds__(256) cg_matvec_kernel(const float* __restrict_
   }
   if (j < P) a0 = fma((double)sr[j], p[j], a0);
   const double a = warp_sum(a0 + a1);
-  if (lane == 0) {
-    q[row] = a;
-    atomicAdd(&ws[1], p[row] * a);
-  }
+  if (lane == 0) q[row] = a;
+}
+// pq = p.q
+__global__ void __launch_bounds__(1024) cg_dot_kernel(const int P, double* __restrict__ ws) {
+  __shared__ double red[32];
+  if (ws[4] != 0.0) return;
+  const double* p = ws + CG_SCAL + 2 * (int64_t)P;
+  const double* q = p + P;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a += p[i] * q[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) ws[1] = a;
 }
 // x += a p ; r -= a q ; z = dinv r ; rz_new += r.z ; rr += r.r
-__global__ void cg_update_kernel(const int P, double* __restrict__ ws) {
+__global__ void __launch_bounds__(1024) cg_update_kernel(const int P, double* __restrict__ ws) {
+  __shared__ double red[32];
   if (ws[4] != 0.0) return;
   double* x = ws + CG_SCAL; double* r = x + P; double* p = r + P; double* q = p + P; double* dinv = q + P;
   const double a = ws[1] != 0.0 ? ws[0] / ws[1] : 0.0;
@@ -312,11 +346,11 @@ __global__ void cg_update_kernel(const int P, double* __restrict__ ws) {
     rz += ri * dinv[i] * ri;
     rr += ri * ri;
   }
-  rz = warp_sum(rz);
-  rr = warp_sum(rr);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&ws[2], rz);
-    atomicAdd(&ws[7], rr);
+  rz = block_sum(rz, red);
+  rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    ws[2] = rz;
+    ws[7] = rr;
   }
 }
 // p = z + b p ; rotate the scalars ; convergence test on |r| / |f|
@@ -444,26 +478,45 @@ int nqmc_sr_update(nqmc_ctx* ctx, float* Ot, const float* e_l, int64_t P, int64_
   double* ws = work;                              // CG_SCAL scalars + x r p q dinv
   double* f = work + CG_SCAL + 5 * P;             // P
   double* sums = f + P;                           // 2 (+ done counter at [2])
+  // With a peer-memory communicator attached the samples are sharded over the ranks: the sample count, the energy sum,
+  // the row sums, f, the diagonal of S and -- every CG iteration -- q = S_r p are summed over ranks in-stream
+  // (nqmc_comm.cu, bitwise identical on all ranks, so every rank takes the same CG steps and ends with the same delta).
+  // S itself is never reduced: each rank keeps its own P x P part.
+  const bool multi = nq_comm_active(ctx);
+  double* rs = ws + CG_SCAL + 3 * P;              // row sums live in q's place until CG starts
   NQMC_CUDA(cudaMemsetAsync(ws, 0, CG_SCAL * sizeof(double), st));
   NQMC_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
   sr_energy_mean_kernel<<<ctx->sm_count, 256, 0, st>>>(e_l, n, sums);
   NQMC_LAUNCH_CHECK();
-  sr_center_kernel<<<(unsigned)P, 256, 0, st>>>(Ot, e_l, n, ld, sums, f);
+  int rc;
+  if (multi && (rc = nq_comm_allreduce(ctx, sums, 8, st))) return rc;
+  sr_rowsum_kernel<<<(unsigned)P, 256, 0, st>>>(Ot, e_l, n, ld, rs);
   NQMC_LAUNCH_CHECK();
-  // S = Oc Oc^T / n_finite + reg I : the epilogue reads n_finite from the device (sums[0]), so nothing synchronises;
-  // the centred rows of non-finite samples are zero and drop out of the sum.
-  int rc = launch_gram(ctx, Ot, Ot, P, P, n, ld, ld, 1.0f / (float)n, reg, 1, S, P, st, sums);
+  if (multi && (rc = nq_comm_allreduce(ctx, rs, P, st))) return rc;
+  sr_center_kernel<<<(unsigned)P, 256, 0, st>>>(Ot, e_l, n, ld, sums, rs, f);
+  NQMC_LAUNCH_CHECK();
+  if (multi && (rc = nq_comm_allreduce(ctx, f, P, st))) return rc;
+  // S_r = Oc Oc^T / n_finite (+ reg I on rank 0 only, so that the sum over ranks carries it once): the epilogue reads
+  // the global n_finite from the device (sums[0]), so nothing synchronises; the centred rows of non-finite samples are
+  // zero and drop out of the sum.
+  const int rank0 = !multi || nq_comm_rank(ctx) == 0;
+  rc = launch_gram(ctx, Ot, Ot, P, P, n, ld, ld, 1.0f / (float)n, rank0 ? reg : 0.0f, 1, S, P, st, sums);
   if (rc != NQMC_OK) return rc;
   const int g = ctx->sm_count;
-  cg_init_kernel<<<g, 256, 0, st>>>(S, P, f, (int)P, ws);
+  cg_diag_kernel<<<g, 256, 0, st>>>(S, P, (int)P, ws);
+  NQMC_LAUNCH_CHECK();
+  if (multi && (rc = nq_comm_allreduce(ctx, ws + CG_SCAL + 4 * P, P, st))) return rc;
+  cg_init_kernel<<<1, 1024, 0, st>>>(f, (int)P, ws);
   NQMC_LAUNCH_CHECK();
   const double tol2 = tol * tol;
   for (int it = 0; it < max_iter; ++it) {
     cg_matvec_kernel<<<(unsigned)((P + 7) / 8), 256, 0, st>>>(S, P, (int)P, ws);
-    cg_update_kernel<<<g, 256, 0, st>>>((int)P, ws);
+    if (multi && (rc = nq_comm_allreduce(ctx, ws + CG_SCAL + 3 * P, P, st))) return rc;
+    cg_dot_kernel<<<1, 1024, 0, st>>>((int)P, ws);
+    cg_update_kernel<<<1, 1024, 0, st>>>((int)P, ws);
     cg_direction_kernel<<<g, 256, 0, st>>>((int)P, tol2, ws, sums + 2);
   }
-  ctx->launches += 3 * (int64_t)max_iter;
+  ctx->launches += 4 * (int64_t)max_iter;
   sr_finish_kernel<<<g, 256, 0, st>>>((int)P, lr, ws, delta, info);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

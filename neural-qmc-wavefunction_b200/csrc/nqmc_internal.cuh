@@ -300,6 +300,7 @@ int nq_comm_create(nqmc_ctx* ctx, int rank, int world, void* handle_out);
 int nq_comm_attach(nqmc_ctx* ctx, const void* handles);
 int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st);
 bool nq_comm_active(const nqmc_ctx* ctx);
+int nq_comm_rank(const nqmc_ctx* ctx);
 void nq_comm_free(nqmc_ctx* ctx);
 int nq_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t S, int64_t W, int n_blocks, double* out, cudaStream_t st);
 int nq_adapt_sigma(nqmc_ctx* ctx, float* n_acc, int64_t W, int steps, float target, float gain, float* sigma_dev,

@@ -125,7 +125,7 @@ class VMCOptimizer:
     target_acceptance: float = 0.5
     optimizer: str = "adam"         # "adam" (the reference's optax chain) or "sr": Stochastic Reconfiguration on the device
                                     # ([SPEC] .github/phase6-issue-body.md:130-182; nqmc_log_psi_grads + nqmc_sr_update),
-                                    # SimpleWavefunction, single GPU; learning_rate is the SR step, clip_grad is unused
+                                    # SimpleWavefunction; over ranks with the peer-memory communicator attached; learning_rate is the SR step, clip_grad unused
     sr_regularization: float = 1e-3
     sr_max_iter: int = 300
     sr_tol: float = 1e-6
@@ -209,8 +209,9 @@ class VMCOptimizer:
             h = hdr.numpy(ctx.stream)
             rank, ws = parallel.world()
             if self.optimizer == "sr":
-                if ws > 1:
-                    raise NotImplementedError("optimizer='sr' is single-GPU (S is not reduced over ranks)")
+                if ws > 1 and not ctx.comm_active():
+                    raise NotImplementedError("optimizer='sr' over several ranks needs the peer-memory communicator "
+                                              "(parallel.attach_peer_memory): its sums run inside nqmc_sr_update")
                 Ot = ctx.log_psi_grads(samples)                               # phase6-issue-body.md:152-165 (O, parameter-major)
                 sr_delta, sr_info, _ = ctx.sr_update(Ot, e, self.sr_regularization, self.learning_rate, self.sr_max_iter,
                                                      self.sr_tol)            # :168-181

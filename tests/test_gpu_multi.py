@@ -23,6 +23,20 @@ def test_peer_memory_allreduce_and_fused_step():
 
 
 @pytest.mark.gpu
+def test_stochastic_reconfiguration_over_ranks():
+    """Samples sharded over the ranks, S never reduced (q = S_r p is, every CG iteration): same update as the fp64 oracle
+    on all samples, bitwise identical on every rank."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "scripts", "check_sr_multi.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert "CHECK_SR_MULTI PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_communicator_single_rank_is_identity_and_validates_arguments():
     """world = 1: create/attach succeed, the all-reduce is the identity; bad arguments are rejected, and the
     all-reduce refuses to run before a communicator is attached (no silent fallback)."""
