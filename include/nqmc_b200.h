@@ -229,7 +229,11 @@ int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t 
  * e_l  : [n] local energies ; S: [P][P] fp32 workspace, on return the regularised S ; work: nqmc_sr_workspace_bytes(P)
  * delta: [P] fp64 update direction (-lr S^-1 f) ; info (may be NULL): [4] = CG iterations, |r|/|f|, converged, |f|
  * The solve is Jacobi-preconditioned CG (S is SPD for reg > 0) run for at most max_iter iterations or until
- * |S x - f| <= tol |f|, entirely in-stream (no host synchronisation). */
+ * |S x - f| <= tol |f|, entirely in-stream (no host synchronisation).
+ * Multi-GPU: with a communicator attached (nqmc_comm_attach) Ot / e_l hold THIS rank's samples; the sample count, the
+ * energy and row sums, f, diag(S) and -- every CG iteration -- S_r p are summed over ranks in-stream (P <= the
+ * communicator's vector length, i.e. the ctx's parameter count); every rank returns the bit-identical delta.  All ranks
+ * must make the call with the same P, max_iter and tol. */
 int64_t nqmc_sr_workspace_bytes(int64_t P);
 /* Per-walker log-derivatives, parameter-major: Ot[p * ld + w] = d log|psi(r_w)| / d theta_p, ld >= W.
  * Replaces: vmap(jax.grad(lambda p: wavefunction(p, r)))(samples) -- src/nqmc/optimizer/vmc.py:120-123 -- in the one
