@@ -278,7 +278,13 @@ __global__ void __launch_bounds__(TCT, 1)
       tmem_ld16(tmem_base + lane_base + C_D + 64u * b + (uint32_t)c0, v);
       uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) split_tf32(nq_tanh(v[j]), hi[j], lo[j]);
+      for (int j = 0; j < UPT; j += 2) {                         // two units per packed instruction (FMUL2 / FADD2 / FFMA2)
+        const float2 h = nq_tanh2(make_float2(v[j], v[j + 1]));
+        const float2 hh = make_float2(__uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u));
+        const float2 ll = nq_add2(h, make_float2(-hh.x, -hh.y));
+        hi[j] = __float_as_uint(hh.x); hi[j + 1] = __float_as_uint(hh.y);
+        lo[j] = __float_as_uint(ll.x); lo[j + 1] = __float_as_uint(ll.y);
+      }
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)c0, hi);
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)(H + c0), lo);
     }
@@ -291,8 +297,13 @@ __global__ void __launch_bounds__(TCT, 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float v[16];
       tmem_ld16(tmem_base + lane_base + C_D + 64u * pb + (uint32_t)c0, v);
+      float2 o2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) out = fmaf(W3s[c0 + j], nq_tanh(v[j] + b2s[c0 + j]), out);
+      for (int j = 0; j < UPT; j += 2) {
+        const float2 h = nq_tanh2(nq_add2(make_float2(v[j], v[j + 1]), *reinterpret_cast<const float2*>(b2s + c0 + j)));
+        o2 = nq_fma2(*reinterpret_cast<const float2*>(W3s + c0 + j), h, o2);
+      }
+      out = o2.x + o2.y;
       if (quarter != 0) outS[(pb * (NQ - 1) + quarter - 1) * ROWS + row] = out;
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // feature and h1 stores of this step
