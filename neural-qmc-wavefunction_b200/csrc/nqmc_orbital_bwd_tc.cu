@@ -8,10 +8,10 @@
 //     h2 = tanh(U2 + b2); dW3 += seed h2; delta2 = seed W3 (1-h2^2)
 //     D1 = delta2 W2^T                          UMMA  M=128 rows, N=64, K=64    A: delta2 in TMEM,      B: W2^T smem
 //     G2 += h1^T delta2                         UMMA  M=128 (64 units used), N=64, K=128 rows          (smem x smem)
-//     GB += delta2^T [f | 1]                    UMMA  M=128 (64 units used), N=16, K=128 rows: ones column -> db2
+//     db2 += sum_rows delta2                    per-thread partial sums in registers (a GEMM until round 2: see gb2)
 //     delta1 = D1 (1-h1^2)
 //     G1^T += delta1^T [f | 1]                  UMMA  M=128 (64 units used), N=16, K=128 rows: dW1^T, ones column -> db1
-// G2 / GB / G1^T accumulate in tensor memory for the whole kernel and are read back once.
+// G2 / G1^T accumulate in tensor memory for the whole kernel and are read back once.
 //
 // Operand layouts.
 //   * "row" operands of U2 / D1 (A[m=row][k=unit]) are written by their owning thread straight into TMEM
@@ -46,7 +46,7 @@ constexpr int NSYNC = TCT;            // threads meeting at the tile barriers: w
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G2 = 128, C_G1 = 192, C_GB = 224, C_AH = 256, C_AL = 320;
+constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G1 = 192, C_AH = 256, C_AL = 320, C_G2 = 384;   // G2: 128 columns (hi-part | lo-part products)
 // K = rows operands of the weight-gradient GEMMs (h1, delta2, delta1): MN-major, SWIZZLE_128B_BASE32B.  Layout as
 // probed on B200 (scripts/exp/mn_major_probe.cu; tf32 MN-major with SWIZZLE_NONE silently yields zeros):
 //   byte(unit, row) = (unit/32) LBO + (row/4) SBO + (row%4) 128 + (((unit%32)/8) ^ (row%4)) 32 + (unit%8) 4
@@ -84,7 +84,7 @@ __host__ __device__ inline SmemMap make_map(int F) {
   m.fT_lo = o; o += NRG * m.rgf;
   m.fstage = o; o += m.n_fu * FS_LD * 4;
   m.pf = o; o += 5 * ROWS * 4;        // next tile: x, y, z, weight, inverse-matrix entry per row (cp.async targets)
-  m.misc = o; o += (F * H + 3 * H + H + 8) * 4 + 64;
+  m.misc = o; o += (F * H + 3 * H + 2 * H + 8) * 4 + 64;
   m.total = o;
   return m;
 }
@@ -100,6 +100,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {   // MN-m
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 // G2: A and B MN-major, M = 64 (the 64 h1 units; half the A-operand traffic of M = 128, same UMMA time).
 // An M = 64 accumulator row u lives in TMEM lane (u / 16) * 32 + u % 16 (probed: scripts/exp/m64_probe.cu).
+// the same with N = 128: B' = [delta2_hi | delta2_lo] (the lo buffer follows the hi buffer: two more 32-unit atom columns), so
+// one UMMA yields a_hi b_hi in columns 0-63 and a_hi b_lo in columns 64-127 -- two UMMAs per k-step instead of three, and
+// the A operand is read from shared memory twice instead of three times (the kernel is shared-memory-bandwidth-bound)
+constexpr uint32_t IDESC_MN128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 constexpr uint32_t IDESC_MN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -191,21 +195,30 @@ __device__ __forceinline__ void stage_rows_tmem(uint32_t t_hi, uint32_t t_lo, co
 }
 
 // 16 values of this thread's row (units c0 .. c0+15) -> tf32 hi / lo in an MN-major swizzled operand buffer:
-// two 32-byte chunks per buffer at byte offsets off0 / off1 (see the layout formula above), straight from registers
-__device__ __forceinline__ void stage_mn(uint8_t* hi, uint8_t* lo, const int off0, const int off1, const float (&v)[16]) {
+// two 32-byte chunks per buffer at byte offsets off0 / off1 (see the layout formula above), straight from registers.
+// Bank conflicts: the 8 lanes of a quarter warp own 8 consecutive rows, i.e. every row % 4 twice, and the chunk index is
+// XORed with row % 4 only -- two lanes per 32-byte chunk slot.  `flip` = bit 2 of the row: lanes with flip set write the
+// upper 16 bytes of their chunk first and the lower ones second, so each STS.128 of a quarter warp covers all 32 banks.
+__device__ __forceinline__ void stage_mn(uint8_t* hi, uint8_t* lo, const int off0, const int off1, const float (&v)[16], const bool flip) {
+  const int of_first = flip ? 16 : 0, of_second = 16 - of_first;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint8_t* ph = hi + (c == 0 ? off0 : off1);
     uint8_t* pl = lo + (c == 0 ? off0 : off1);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h) {                 // h = 0: this lane's first store, h = 1: its second
+      const int a = 8 * c, b = 8 * c + 4;
+      const bool upper = (h == 1) != flip;        // which half of the chunk this store carries
+      const float x0 = upper ? v[b + 0] : v[a + 0], x1 = upper ? v[b + 1] : v[a + 1];
+      const float x2 = upper ? v[b + 2] : v[a + 2], x3 = upper ? v[b + 3] : v[a + 3];
       float4 h4, l4;
-      split_tf32(v[8 * c + 4 * h + 0], h4.x, l4.x);
-      split_tf32(v[8 * c + 4 * h + 1], h4.y, l4.y);
-      split_tf32(v[8 * c + 4 * h + 2], h4.z, l4.z);
-      split_tf32(v[8 * c + 4 * h + 3], h4.w, l4.w);
-      *reinterpret_cast<float4*>(ph + 16 * h) = h4;
-      *reinterpret_cast<float4*>(pl + 16 * h) = l4;
+      split_tf32(x0, h4.x, l4.x);
+      split_tf32(x1, h4.y, l4.y);
+      split_tf32(x2, h4.z, l4.z);
+      split_tf32(x3, h4.w, l4.w);
+      const int of = h == 0 ? of_first : of_second;
+      *reinterpret_cast<float4*>(ph + of) = h4;
+      *reinterpret_cast<float4*>(pl + of) = l4;
     }
   }
 }
@@ -225,8 +238,8 @@ __global__ void __launch_bounds__(TCT, 1)
   float* b1s = W1s + F * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
-  float* redS = W3s + H;             // [H + 8]: dW3[H], db3
-  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + H + 8);   // 4 mbarriers
+  float* redS = W3s + H;             // [2H + 8]: dW3[H], db3 (+7 pad), db2[H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + 2 * H + 8);   // 4 mbarriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* fstage = reinterpret_cast<float*>(smem + mp.fstage);   // [n_fu][ROWS]
 
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(TCT, 1)
     b2s[q] = theta[off.b2 + q];
     W3s[q] = theta[off.W3 + q];
   }
-  for (int q = tid; q < H + 8; q += TCT) redS[q] = 0.f;
+  for (int q = tid; q < 2 * H + 8; q += TCT) redS[q] = 0.f;
   {
     // all loads of a thread in flight at once: with a cold L2 each dependent round trip costs ~1 us
     constexpr int NL = H * H / TCW;
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   __syncthreads();
   if (tid == 0) {
-    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(b == 2 ? 2 : 1));   // bar_g2: G2 and GB issuers
+    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -302,11 +315,18 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
   for (int j = 0; j < UPT; ++j) gW3[j] = 0.f;
   float gb3 = 0.f;
+  // db2 = sum over rows of delta2: per-thread partial sums, reduced once at the end like dW3.  (Until round 2 this was a
+  // fourth tensor-core GEMM, delta2^T [f|1], whose 48 UMMAs re-read the whole delta2 operand from shared memory for one
+  // useful output column; the kernel is shared-memory-bandwidth-bound -- LSU + tensor-core wavefronts at 90 % of peak.)
+  float gb2[UPT];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) gb2[j] = 0.f;
   const int c0 = UPT * quarter;                     // first hidden unit / output column of this thread
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // byte offsets of this thread's two 32-byte chunks (units c0..c0+7, c0+8..c0+15 of its row) in an MN-major buffer
   const int mn_row = (quarter >> 1) * MN_LBO + (row >> 2) * MN_SBO + (row & 3) * 128, mn_cb = 2 * (quarter & 1);
   const int mn_off0 = mn_row + ((mn_cb ^ (row & 3)) << 5), mn_off1 = mn_row + (((mn_cb + 1) ^ (row & 3)) << 5);
+  const bool mn_flip = (row & 4) != 0;
   uint8_t* hM_hi = smem + mp.hM_hi;
   uint8_t* hM_lo = smem + mp.hM_lo;
   uint8_t* dM_hi = smem + mp.dM_hi;
@@ -349,9 +369,9 @@ __global__ void __launch_bounds__(TCT, 1)
   // wait for G2(t) -- which still reads the buffer delta1^T goes into -- hides behind layer 1 of tile t+1):
   //   P1  layer 1(t) -> A(h1) in TMEM ; delta1(t-1) -> dM                   | issue U2(t), G1^T(t-1) = delta1^T [f|1]
   //   P2  h1(t) -> hM ; wait U2 ; h2, dW3, delta2 -> A(delta2) in TMEM        | issue D1(t)
-  //   P3  wait G1^T(t-1) ; delta2(t) -> dM ; features(t) -> fT              | issue G2(t) = h1^T delta2, GB(t) = delta2^T [f|1]
+  //   P3  wait G1^T(t-1) ; delta2(t) -> dM ; features(t) -> fT              | issue G2(t) = h1^T delta2
   //   P4  wait D1 ; delta1(t) = D1 (1 - h1^2)  (registers)
-  // The ones column of [f|1] yields db1 (from G1^T) and db2 (from GB).
+  // The ones column of [f|1] yields db1 (from G1^T); db2 is summed in registers.
   float d1[UPT];
 #pragma unroll
   for (int j = 0; j < UPT; ++j) d1[j] = 0.f;
@@ -373,7 +393,7 @@ __global__ void __launch_bounds__(TCT, 1)
     // =============================== issuer warpgroup ========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     // The four warps of this warpgroup share the issue work (one thread sustains only about one tcgen05.mma per 100
-    // cycles, scripts/exp/mma_rate.cu): warp 0: U2, D1 (the critical chain) ; 1: G1^T ; 2: G2 ; 3: GB.
+    // cycles, scripts/exp/mma_rate.cu): warp 0: U2, D1 (the critical chain) ; 1: G1^T ; 2: G2 ; 3: idle.
     const int iw = warp - ISSUER;
     const uint32_t leader = elect_one();
     int64_t n_done = 0;
@@ -412,18 +432,14 @@ __global__ void __launch_bounds__(TCT, 1)
       tile_barrier();                                    // P3 done: h1 in hM, delta2 in dM, features in fT
       if (iw == 2) {
         const uint64_t ah = umma_desc_mn(sbase + mp.hM_hi), al = umma_desc_mn(sbase + mp.hM_lo);
-        const uint64_t bh = umma_desc_mn(sbase + mp.dM_hi), bl = umma_desc_mn(sbase + mp.dM_lo);
+        const uint64_t bh = umma_desc_mn(sbase + mp.dM_hi);   // N = 128 reads on into dM_lo (contiguous: see SmemMap)
 #pragma unroll 1
         for (int ks = 0; ks < ROWS / 8; ++ks) {          // G2 += h1^T delta2   (both operands MN-major, K = 8 rows per UMMA)
           const uint64_t ko = (uint64_t)((ks * 2 * MN_SBO) >> 4);
           const uint32_t acc = (n_done == 0 && ks == 0) ? 0u : 1u;
-          umma_ss(tmem_base + C_G2, ah + ko, bh + ko, IDESC_MN, acc, leader);
-          umma_ss(tmem_base + C_G2, al + ko, bh + ko, IDESC_MN, 1u, leader);
-          umma_ss(tmem_base + C_G2, ah + ko, bl + ko, IDESC_MN, 1u, leader);
+          umma_ss(tmem_base + C_G2, ah + ko, bh + ko, IDESC_MN128, acc, leader);   // a_hi [b_hi | b_lo]
+          umma_ss(tmem_base + C_G2, al + ko, bh + ko, IDESC_MN, 1u, leader);       // a_lo b_hi -> columns 0-63
         }
-        umma_commit(bar_g2, leader);
-      } else if (iw == 3) {
-        issue_df(C_GB, leader, n_done == 0);             // GB += delta2^T [f|1]: its ones column is db2
         umma_commit(bar_g2, leader);
       }
     }
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(TCT, 1)
       if (n_done > 0) {
         mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
         ph_g2 ^= 1;
-        stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1);
+        stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1, mn_flip);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
     }
@@ -507,7 +523,7 @@ __global__ void __launch_bounds__(TCT, 1)
     tile_barrier();
     // ======== P2 ========
     if (worker) {
-      stage_mn(hM_hi, hM_lo, mn_off0, mn_off1, h1);         // G2(t-1), the reader of this buffer, was waited for in P1
+      stage_mn(hM_hi, hM_lo, mn_off0, mn_off1, h1, mn_flip);         // G2(t-1), the reader of this buffer, was waited for in P1
       mbar_wait(bar_u, ph_u);
       ph_u ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -519,6 +535,8 @@ __global__ void __launch_bounds__(TCT, 1)
         gW3[j] = fmaf(seed, h, gW3[j]);
         v[j] = seed * W3s[c0 + j] * fmaf(-h, h, 1.0f);
       }
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) gb2[j] += v[j];
       if (quarter == 0) gb3 += seed;
       stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, v);
 #pragma unroll
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(TCT, 1)
       const bool more = item + n_chunks < n_items;
       if (more && quarter == 0) fetch(item + n_chunks);         // next tile's positions / seed (read last in P1, two barriers ago)
       if (n_done > 0) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }   // G1(t-1) reads delta1^T(t-1) and the features of tile t-1
-      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d2);
+      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d2, mn_flip);
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]
       for (int idx = tid; idx < mp.n_fu * NRG; idx += TCW) {
         const int g = idx / mp.n_fu, f = idx % mp.n_fu;     // consecutive lanes: consecutive 16-byte granules
@@ -564,7 +582,7 @@ __global__ void __launch_bounds__(TCT, 1)
     if (worker) {
       mbar_wait(bar_g2, ph_g2);
       ph_g2 ^= 1;
-      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1);
+      stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1, mn_flip);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -580,7 +598,11 @@ __global__ void __launch_bounds__(TCT, 1)
       mbar_wait(bar_g, ph_g);                            // the last commit: every MMA of this CTA has completed
       ph_g ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float v2l[16];
       tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)c0, v2);   // lane = h1 unit
+      tmem_ld16(tmem_base + lane_base + C_G2 + (uint32_t)(H + c0), v2l);   // the a_hi b_lo products
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) v2[j] += v2l[j];
     } else {
 #pragma unroll
       for (int j = 0; j < UPT; ++j) v2[j] = 0.f;          // this CTA had no tile: the slab must still be defined
@@ -592,16 +614,15 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
       for (int j = 0; j < UPT; ++j) slab[o_W2 + unit * H + c0 + j] = v2[j];
     }
-    // G1^T / GB: lane = delta1 / delta2 unit, column = feature (column F: ones -> db1 / db2); 8 columns per read,
+    // G1^T: lane = delta1 unit, column = feature (column F: ones -> db1); 8 columns per read,
     // column groups dealt over the quarters
     for (int cg = quarter; cg < mp.n_g1 / 8; cg += NQ) {
-      float v1[8], vb[8];
+      float v1[8];
       if (any) {
         tmem_ld8(tmem_base + lane_base + C_G1 + (uint32_t)(8 * cg), v1);
-        tmem_ld8(tmem_base + lane_base + C_GB + (uint32_t)(8 * cg), vb);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v1[j] = vb[j] = 0.f;
+        for (int j = 0; j < 8; ++j) v1[j] = 0.f;
       }
       if (lane_ok) {
 #pragma unroll
@@ -610,7 +631,6 @@ __global__ void __launch_bounds__(TCT, 1)
           if (f < F) slab[o_W1 + f * H + unit] = v1[j];
           else if (f == F) {
             slab[o_b1 + unit] = v1[j];
-            slab[o_b2 + unit] = vb[j];
           }
         }
       }
@@ -619,6 +639,8 @@ __global__ void __launch_bounds__(TCT, 1)
     for (int j = 0; j < UPT; ++j) {                     // dW3 / db3: reduce the per-row partials over the 128 rows
       const float t = warp_sum(gW3[j]);
       if ((tid & 31) == 0) atomicAdd(&redS[c0 + j], t);
+      const float t2 = warp_sum(gb2[j]);
+      if ((tid & 31) == 0) atomicAdd(&redS[H + 8 + c0 + j], t2);
     }
     if (quarter == 0) {
       const float t = warp_sum(gb3);
@@ -627,7 +649,10 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tile_barrier();
-  for (int q = tid; q < H; q += TCW) slab[o_W3 + q] = redS[q];
+  for (int q = tid; q < H; q += TCW) {
+    slab[o_W3 + q] = redS[q];
+    slab[o_b2 + q] = redS[H + 8 + q];
+  }
   if (tid == 0) slab[o_b3] = redS[H];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
