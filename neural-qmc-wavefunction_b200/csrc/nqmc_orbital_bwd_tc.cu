@@ -46,7 +46,7 @@ constexpr int NSYNC = TCT;            // threads meeting at the tile barriers: w
 constexpr int ROWS = 128;
 constexpr int UPT = H / NQ;           // hidden units / output columns per thread = 16
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G1 = 192, C_AH = 256, C_AL = 320, C_G2 = 384;   // G2: 128 columns (hi-part | lo-part products)
+constexpr uint32_t C_U2 = 0, C_D1 = 64, C_G1 = 192, C_F1 = 224, C_AH = 256, C_AL = 320, C_G2 = 384;   // C_F1: layer-1 features, hi 16 + lo 16 columns   // G2: 128 columns (hi-part | lo-part products)
 // K = rows operands of the weight-gradient GEMMs (h1, delta2, delta1): MN-major, SWIZZLE_128B_BASE32B.  Layout as
 // probed on B200 (scripts/exp/mn_major_probe.cu; tf32 MN-major with SWIZZLE_NONE silently yields zeros):
 //   byte(unit, row) = (unit/32) LBO + (row/4) SBO + (row%4) 128 + (((unit%32)/8) ^ (row%4)) 32 + (unit%8) 4
@@ -62,11 +62,13 @@ constexpr int NRG = ROWS / 4;         // 32 row groups (granule = 4 consecutive 
 constexpr int WB = (H / 4) * H * 16;  // one W2 copy (hi or lo)                                                   = 16384 B
 
 struct SmemMap {      // byte offsets, computed from F at run time (identical on host and device)
-  int hM_hi, hM_lo, dM_hi, dM_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, fstage, pf, misc, total;
+  int hM_hi, hM_lo, dM_hi, dM_lo, fT_hi, fT_lo, wa_hi, wa_lo, wb_hi, wb_lo, w1_hi, w1_lo, fstage, pf, misc, total;
   int n_fu, rgf;      // feature units incl. ones, padded to 4 ; row-group stride of the (K-major) feature buffer
   int n_g1;           // N of the [f|1] MMAs (a multiple of 8): columns >= n_fu read into the next row group, ignored
 };
-__host__ __device__ inline SmemMap make_map(int F) {
+constexpr int K1 = 16;                // K of the layer-1 UMMAs: x, y, z, 1, (d_a, exp(-d_a)) pairs, zero padding (A <= 4 ... 6)
+constexpr int W1B = (K1 / 4) * H * 16; // one [W1; b1] operand copy (hi or lo): 4 KB
+__host__ __device__ inline SmemMap make_map(int F, bool l1tc = false) {
   SmemMap m;
   m.n_fu = 4 * ((F + 1 + 3) / 4);
   m.n_g1 = 8 * ((F + 1 + 7) / 8);
@@ -82,9 +84,11 @@ __host__ __device__ inline SmemMap make_map(int F) {
   m.wb_lo = o; o += WB;
   m.fT_hi = o; o += NRG * m.rgf;
   m.fT_lo = o; o += NRG * m.rgf;
+  m.w1_hi = o; o += l1tc ? W1B : 0;
+  m.w1_lo = o; o += l1tc ? W1B : 0;
   m.fstage = o; o += m.n_fu * FS_LD * 4;
   m.pf = o; o += 5 * ROWS * 4;        // next tile: x, y, z, weight, inverse-matrix entry per row (cp.async targets)
-  m.misc = o; o += (F * H + 3 * H + 2 * H + 8) * 4 + 64;
+  m.misc = o; o += (F * H + 3 * H + 2 * H + 8) * 4 + 80;
   m.total = o;
   return m;
 }
@@ -232,15 +236,21 @@ __global__ void __launch_bounds__(TCT, 1)
                       const int p_mlp) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int A = NA > 0 ? NA : s.A, F = 3 + 2 * A;
-  const SmemMap mp = make_map(F);
+  // Layer 1 on the tensor cores (A <= 4: the operand copies fit next to everything else in shared memory): the row's four
+  // threads write [x, y, z, 1, d_a, exp(-d_a) ...] as tf32 hi / lo straight into TMEM (one nucleus each), six UMMAs form
+  // [f|1] [W1; b1] in the (still free) U2 columns, and a thread gets its 16 pre-activations with one tcgen05.ld instead of
+  // 11 x 16 FFMAs behind 44 broadcast LDS.128 -- measured with clock64 stamps, the FP32 layer 1 was 2.7 k of a tile's
+  // 9.3 k cycles.  The wait for G2(t-1) and the delta1 staging run while those UMMAs are in flight.
+  constexpr bool L1TC = NA >= 1 && NA <= 4;
+  const SmemMap mp = make_map(F, L1TC);
   float* misc = reinterpret_cast<float*>(smem + mp.misc);
   float* W1s = misc;                 // [F][H]
   float* b1s = W1s + F * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
   float* redS = W3s + H;             // [2H + 8]: dW3[H], db3 (+7 pad), db2[H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + 2 * H + 8);   // 4 mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(redS + 2 * H + 8);   // 5 mbarriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* fstage = reinterpret_cast<float*>(smem + mp.fstage);   // [n_fu][ROWS]
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -265,6 +275,20 @@ __global__ void __launch_bounds__(TCT, 1)
     W3s[q] = theta[off.W3 + q];
   }
   for (int q = tid; q < 2 * H + 8; q += TCT) redS[q] = 0.f;
+  if constexpr (L1TC) {
+    for (int idx = tid; idx < K1 * H; idx += TCT) {
+      const int k = idx / H, n = idx % H;   // operand feature order: x, y, z, 1, then (d_a, exp(-d_a)) pairs
+      float v = 0.f;
+      if (k < 3) v = theta[off.W1 + k * H + n];
+      else if (k == 3) v = theta[off.b1 + n];
+      else if (k < 4 + 2 * A) v = theta[off.W1 + (((k - 4) & 1) ? 3 + A + ((k - 4) >> 1) : 3 + ((k - 4) >> 1)) * H + n];
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      const int o = (k >> 2) * (H * 4) + n * 4 + (k & 3);
+      reinterpret_cast<float*>(smem + mp.w1_hi)[o] = hi;
+      reinterpret_cast<float*>(smem + mp.w1_lo)[o] = lo;
+    }
+  }
   {
     // all loads of a thread in flight at once: with a cold L2 each dependent round trip costs ~1 us
     constexpr int NL = H * H / TCW;
@@ -291,7 +315,7 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   __syncthreads();
   if (tid == 0) {
-    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(1));
+    for (int b = 0; b < 5; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -306,7 +330,8 @@ __global__ void __launch_bounds__(TCT, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_u = smem_u32(&bars[0]), bar_d = smem_u32(&bars[1]), bar_g2 = smem_u32(&bars[2]), bar_g = smem_u32(&bars[3]);
-  uint32_t ph_u = 0, ph_d = 0, ph_g2 = 0, ph_g = 0;
+  const uint32_t bar_l1 = smem_u32(&bars[4]);
+  uint32_t ph_u = 0, ph_d = 0, ph_g2 = 0, ph_g = 0, ph_l1 = 0;
   nq_pdl_wait();                              // everything above read theta only; header, E_L, inverses come from predecessors
   float centerf = 0.f;
   if (hdr != nullptr) centerf = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
@@ -398,6 +423,22 @@ __global__ void __launch_bounds__(TCT, 1)
     const uint32_t leader = elect_one();
     int64_t n_done = 0;
     for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
+      if constexpr (L1TC) {
+        tile_barrier();                                  // P0 done: features of this tile in TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (iw == 0) {                                   // Z1 = [f|1] [W1; b1] into the U2 columns (free until U2 is issued)
+          const uint64_t bh = umma_desc(sbase + mp.w1_hi, H * 16, 128), bl = umma_desc(sbase + mp.w1_lo, H * 16, 128);
+#pragma unroll
+          for (int ks = 0; ks < K1 / 8; ++ks) {
+            const uint64_t bo = (uint64_t)((ks * 2 * H * 16) >> 4);
+            const uint32_t ah = tmem_base + C_F1 + 8 * ks, al = tmem_base + C_F1 + K1 + 8 * ks;
+            umma_ts(tmem_base + C_U2, ah, bh + bo, ks == 0 ? 0u : 1u, leader);
+            umma_ts(tmem_base + C_U2, al, bh + bo, 1u, leader);
+            umma_ts(tmem_base + C_U2, ah, bl + bo, 1u, leader);
+          }
+          umma_commit(bar_l1, leader);
+        }
+      }
       tile_barrier();                                    // P1 done: A(h1) in TMEM, delta1(t-1) in dM
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (iw == 0) {
@@ -456,6 +497,14 @@ __global__ void __launch_bounds__(TCT, 1)
   }
   // =============================== worker warps ================================================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+  if constexpr (L1TC) {                                // the padding feature columns (4 + 2A .. 15, hi and lo) must read as zero
+    if (worker && quarter == 0) {
+      const uint32_t z[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st16(tmem_base + lane_base + C_F1, z);
+      tmem_st16(tmem_base + lane_base + C_F1 + 16u, z);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+  }
   int64_t n_done = 0;                                  // tiles this CTA has completed
   for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
     float h1[UPT], d2[UPT], seed = 0.f;
@@ -469,54 +518,105 @@ __global__ void __launch_bounds__(TCT, 1)
         seed = wt * ninv;
         if ((item / ns) * ROWS + row >= W || !isfinite(seed)) seed = 0.f;
       }
-#pragma unroll
-      for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
-      const float pc[3] = {x, y, z};
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-#pragma unroll
-        for (int v = 0; v < UPT / 4; ++v) {
-          const float4 wv = *reinterpret_cast<const float4*>(W1s + d * H + c0 + 4 * v);
-          h1[4 * v + 0] = fmaf(pc[d], wv.x, h1[4 * v + 0]);
-          h1[4 * v + 1] = fmaf(pc[d], wv.y, h1[4 * v + 1]);
-          h1[4 * v + 2] = fmaf(pc[d], wv.z, h1[4 * v + 2]);
-          h1[4 * v + 3] = fmaf(pc[d], wv.w, h1[4 * v + 3]);
-        }
-      }
-      if (quarter == 0) {
-        fstage[0 * FS_LD + row] = x;
-        fstage[1 * FS_LD + row] = y;
-        fstage[2 * FS_LD + row] = z;
-        fstage[F * FS_LD + row] = 1.0f;                  // ones unit -> db1
-      }
-#pragma unroll
-      for (int a = 0; a < A; ++a) {
-        const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
-        const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        const float ex = __expf(-dd);
+      if constexpr (L1TC) {
+        // P0: this thread's share of the row's features -> TMEM (operand order x, y, z, 1, (d_a, e_a) pairs) and -> fstage
+        // (reference order, the B operand of G1)
+        const uint32_t fa = tmem_base + lane_base + C_F1;
         if (quarter == 0) {
+          float hx, lx, hy, ly, hz, lz;
+          split_tf32(x, hx, lx);
+          split_tf32(y, hy, ly);
+          split_tf32(z, hz, lz);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(fa), "r"(__float_as_uint(hx)),
+                       "r"(__float_as_uint(hy)), "r"(__float_as_uint(hz)), "r"(0x3f800000u) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(fa + K1), "r"(__float_as_uint(lx)),
+                       "r"(__float_as_uint(ly)), "r"(__float_as_uint(lz)), "r"(0u) : "memory");
+          fstage[0 * FS_LD + row] = x;
+          fstage[1 * FS_LD + row] = y;
+          fstage[2 * FS_LD + row] = z;
+          fstage[F * FS_LD + row] = 1.0f;                // ones unit -> db1
+        }
+        if (quarter < A) {                               // A <= 4: nucleus `quarter`
+          const int a = quarter;
+          const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+          const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float ex = __expf(-dd);
+          float hd, ld, he, le;
+          split_tf32(dd, hd, ld);
+          split_tf32(ex, he, le);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(fa + (uint32_t)(4 + 2 * a)),
+                       "r"(__float_as_uint(hd)), "r"(__float_as_uint(he)) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(fa + (uint32_t)(K1 + 4 + 2 * a)),
+                       "r"(__float_as_uint(ld)), "r"(__float_as_uint(le)) : "memory");
           fstage[(3 + a) * FS_LD + row] = dd;
           fstage[(3 + A + a) * FS_LD + row] = ex;
         }
-#pragma unroll
-        for (int v = 0; v < UPT / 4; ++v) {
-          const float4 wd = *reinterpret_cast<const float4*>(W1s + (3 + a) * H + c0 + 4 * v);
-          const float4 we = *reinterpret_cast<const float4*>(W1s + (3 + A + a) * H + c0 + 4 * v);
-          h1[4 * v + 0] = fmaf(dd, wd.x, fmaf(ex, we.x, h1[4 * v + 0]));
-          h1[4 * v + 1] = fmaf(dd, wd.y, fmaf(ex, we.y, h1[4 * v + 1]));
-          h1[4 * v + 2] = fmaf(dd, wd.z, fmaf(ex, we.z, h1[4 * v + 2]));
-          h1[4 * v + 3] = fmaf(dd, wd.w, fmaf(ex, we.w, h1[4 * v + 3]));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tile_barrier();                                  // issuer: Z1 = [f|1] [W1; b1]
+        if (n_done > 0) {                                // while those UMMAs are in flight:
+          mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
+          ph_g2 ^= 1;
+          stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1, mn_flip);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-      }
+        mbar_wait(bar_l1, ph_l1);
+        ph_l1 ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_ld16(tmem_base + lane_base + C_U2 + (uint32_t)c0, h1);
 #pragma unroll
-      for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
-      // A operand of U2: straight into tensor memory (its previous reader, D1 of the last tile, has completed)
-      stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
-      if (n_done > 0) {
-        mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
-        ph_g2 ^= 1;
-        stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1, mn_flip);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
+        stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) h1[j] = b1s[c0 + j];
+        const float pc[3] = {x, y, z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+          for (int v = 0; v < UPT / 4; ++v) {
+            const float4 wv = *reinterpret_cast<const float4*>(W1s + d * H + c0 + 4 * v);
+            h1[4 * v + 0] = fmaf(pc[d], wv.x, h1[4 * v + 0]);
+            h1[4 * v + 1] = fmaf(pc[d], wv.y, h1[4 * v + 1]);
+            h1[4 * v + 2] = fmaf(pc[d], wv.z, h1[4 * v + 2]);
+            h1[4 * v + 3] = fmaf(pc[d], wv.w, h1[4 * v + 3]);
+          }
+        }
+        if (quarter == 0) {
+          fstage[0 * FS_LD + row] = x;
+          fstage[1 * FS_LD + row] = y;
+          fstage[2 * FS_LD + row] = z;
+          fstage[F * FS_LD + row] = 1.0f;                  // ones unit -> db1
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+          const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          const float ex = __expf(-dd);
+          if (quarter == 0) {
+            fstage[(3 + a) * FS_LD + row] = dd;
+            fstage[(3 + A + a) * FS_LD + row] = ex;
+          }
+#pragma unroll
+          for (int v = 0; v < UPT / 4; ++v) {
+            const float4 wd = *reinterpret_cast<const float4*>(W1s + (3 + a) * H + c0 + 4 * v);
+            const float4 we = *reinterpret_cast<const float4*>(W1s + (3 + A + a) * H + c0 + 4 * v);
+            h1[4 * v + 0] = fmaf(dd, wd.x, fmaf(ex, we.x, h1[4 * v + 0]));
+            h1[4 * v + 1] = fmaf(dd, wd.y, fmaf(ex, we.y, h1[4 * v + 1]));
+            h1[4 * v + 2] = fmaf(dd, wd.z, fmaf(ex, we.z, h1[4 * v + 2]));
+            h1[4 * v + 3] = fmaf(dd, wd.w, fmaf(ex, we.w, h1[4 * v + 3]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) h1[j] = nq_tanh(h1[j]);
+        // A operand of U2: straight into tensor memory (its previous reader, D1 of the last tile, has completed)
+        stage_rows_tmem(tmem_base + lane_base + C_AH + (uint32_t)c0, tmem_base + lane_base + C_AL + (uint32_t)c0, h1);
+        if (n_done > 0) {
+          mbar_wait(bar_g2, ph_g2);                      // G2(t-1) read delta2^T from the buffer delta1^T goes into
+          ph_g2 ^= 1;
+          stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d1, mn_flip);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -686,7 +786,7 @@ int nq_launch_orb_bwd_tc(nqmc_ctx* ctx, const float* r, const float* wgt, const 
                          int* n_chunks_out, cudaStream_t st) {
   const DevSys& s = ctx->sys;
   if (s.H != H) return NQMC_ERR_UNSUPPORTED;
-  const SmemMap mp = make_map(s.F);
+  const SmemMap mp = make_map(s.F, s.A >= 1 && s.A <= 4);   // must match the kernel's L1TC (template NA = s.A for these)
   if (mp.total > SMEM_LIMIT || mp.n_g1 > 32) return NQMC_ERR_UNSUPPORTED;   // too many nuclei for this variant's smem plan
   if (const char* e = getenv("NQMC_TC_BWD"))
     if (atoi(e) == 0) return NQMC_ERR_UNSUPPORTED;
