@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--bond_length", type=float, default=1.4)
     ap.add_argument("--log_every", type=int, default=10)
     ap.add_argument("--ansatz", default="simple", choices=["simple", "slater"])
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "sr"],
+                    help="sr: Stochastic Reconfiguration on the device (simple ansatz; try --lr 0.05 --n_chains 512 --n_samples 8)")
+    ap.add_argument("--sr_regularization", type=float, default=1e-3)
     a = ap.parse_args()
     hidden = tuple(int(x) for x in a.hidden_dims.split(","))
     mol = hydrogen_molecule(a.bond_length)
@@ -43,7 +46,8 @@ def main():
     else:
         wf = AntisymmetricWavefunction(1, 1, hidden, molecule=mol)
         params = wf.init(init_key)
-    opt = VMCOptimizer(learning_rate=a.lr, n_samples=a.n_samples, n_chains=a.n_chains, n_burn=300, step_size=0.2, clip_grad=1.0)
+    opt = VMCOptimizer(learning_rate=a.lr, n_samples=a.n_samples, n_chains=a.n_chains, n_burn=300, step_size=0.2, clip_grad=1.0,
+                       optimizer=a.optimizer, sr_regularization=a.sr_regularization)
     t0 = time.time()
     params, history = opt.train(train_key, wf, params, mol, n_steps=a.n_steps, log_every=a.log_every)
     dt = time.time() - t0
