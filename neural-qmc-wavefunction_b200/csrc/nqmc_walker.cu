@@ -485,14 +485,21 @@ __global__ void stats_finish_kernel(const double* __restrict__ part, const int n
 // ---------------------------------------------------------------------------------------------
 // weighted parameter gradients of the per-walker terms (Jastrow scalars, cusp networks)
 //   out[p] = sum_w weight_w * d(J + C)/d theta_p
+// grid (walker blocks, nuclei): block (bx, a) handles the e-n cusp network of nucleus a for its walkers; blocks with a == 0
+// also take the Jastrow / e-e cusp scalars.  Inside a block the sums over the electrons are formed per thread first and
+// the warp reductions follow per (nucleus, hidden unit) -- not per (electron, nucleus, hidden unit) as in round 1, where
+// the shuffles were 90 % of the kernel (436 us at 32,768 walkers, H6; now grid.y = A blocks each doing 1/6 of 1/6).
 __global__ void __launch_bounds__(WT) walker_grads_kernel(const DevSys s, const float* __restrict__ theta,
                                                           const float* __restrict__ r, const float* __restrict__ wgt,
                                                           const double* __restrict__ hdr, const float* __restrict__ e_l,
                                                           const int64_t W, double* __restrict__ part,
                                                           const int n_slots) {
-  extern __shared__ float sacc[];     // [n_slots] block accumulators
+  extern __shared__ float sacc[];     // [n_slots] block accumulators, then [2][NQMC_MAX_ELEC][WT] distances / exponentials
+  float* sd = sacc + ((n_slots + 3) & ~3);
+  float* se = sd + NQMC_MAX_ELEC * WT;
   for (int q = threadIdx.x; q < n_slots; q += WT) sacc[q] = 0.f;
   __syncthreads();
+  const int an = blockIdx.y;          // this block's nucleus
   float center = 0.f;
   if (hdr) center = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
   const float a_ee = theta[s.jas_a_ee], b_ee = theta[s.jas_b_ee];
@@ -507,64 +514,83 @@ __global__ void __launch_bounds__(WT) walker_grads_kernel(const DevSys s, const 
       else if (e_l) { float e = e_l[w]; wt = isfinite(e) ? e - center : 0.f; }
       else wt = 1.f;
     }
-    float g_aee = 0.f, g_bee = 0.f, g_aen = 0.f, g_ben = 0.f, g_cb = 0.f;
-    for (int i = 0; i < s.N; ++i) {
-      const float xi = r[(int64_t)(3 * i) * W + wc], yi = r[(int64_t)(3 * i + 1) * W + wc], zi = r[(int64_t)(3 * i + 2) * W + wc];
-      for (int j = i + 1; j < s.N; ++j) {
-        float dx = xi - r[(int64_t)(3 * j) * W + wc], dy = yi - r[(int64_t)(3 * j + 1) * W + wc], dz = zi - r[(int64_t)(3 * j + 2) * W + wc];
-        float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        float q = 1.0f / fmaf(b_ee, d, 1.0f);
-        g_aee = fmaf(d, q, g_aee);
-        g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
-        if (s.use_cusp) {
-          const bool same = (i < s.n_up) == (j < s.n_up);
-          float q2 = 1.0f / fmaf(fabsf(cbs), d, 1.0f);
-          g_cb = fmaf(-(same ? s.cusp_same : s.cusp_diff) * d * d, q2 * q2, g_cb);
-        }
-      }
-      for (int a = 0; a < s.A; ++a) {
-        float dx = xi - s.R[3 * a], dy = yi - s.R[3 * a + 1], dz = zi - s.R[3 * a + 2];
-        float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        float q = 1.0f / fmaf(b_en, d, 1.0f);
-        g_aen = fmaf(d, q, g_aen);
-        g_ben = fmaf(-a_en * d * d, q * q, g_ben);
-        if (s.use_cusp) {
-          // slots: 5 + a*81 + {b0[16], W0[3][16], b1, W1[16]} in *theta leaf order* of the nucleus
-          const float e = __expf(-d);
-          const float* W0 = theta + s.en_cusp_W0[a];
-          const float* b0 = theta + s.en_cusp_b0[a];
-          const float* W1 = theta + s.en_cusp_W1[a];
-          const int base = 5 + a * 81;
-          const float wd = wt * d;
-          float sb1 = warp_sum(wd);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[base + 64], sb1);
-          for (int h = 0; h < NQMC_CUSP_H; ++h) {
-            float zt = fmaf(W0[h], d, fmaf(W0[NQMC_CUSP_H + h], d * d, fmaf(W0[2 * NQMC_CUSP_H + h], e, b0[h])));
-            float t = nq_tanh(zt);
-            float dz_ = wd * W1[h] * fmaf(-t, t, 1.0f);
-            float v0 = warp_sum(dz_), v1 = warp_sum(dz_ * d), v2 = warp_sum(dz_ * d * d), v3 = warp_sum(dz_ * e),
-                  v4 = warp_sum(wd * t);
-            if ((threadIdx.x & 31) == 0) {
-              atomicAdd(&sacc[base + h], v0);
-              atomicAdd(&sacc[base + 16 + h], v1);
-              atomicAdd(&sacc[base + 32 + h], v2);
-              atomicAdd(&sacc[base + 48 + h], v3);
-              atomicAdd(&sacc[base + 65 + h], v4);
-            }
+    if (an == 0) {
+      float g_aee = 0.f, g_bee = 0.f, g_aen = 0.f, g_ben = 0.f, g_cb = 0.f;
+      for (int i = 0; i < s.N; ++i) {
+        const float xi = r[(int64_t)(3 * i) * W + wc], yi = r[(int64_t)(3 * i + 1) * W + wc], zi = r[(int64_t)(3 * i + 2) * W + wc];
+        for (int j = i + 1; j < s.N; ++j) {
+          float dx = xi - r[(int64_t)(3 * j) * W + wc], dy = yi - r[(int64_t)(3 * j + 1) * W + wc], dz = zi - r[(int64_t)(3 * j + 2) * W + wc];
+          float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          float q = 1.0f / fmaf(b_ee, d, 1.0f);
+          g_aee = fmaf(d, q, g_aee);
+          g_bee = fmaf(-a_ee * d * d, q * q, g_bee);
+          if (s.use_cusp) {
+            const bool same = (i < s.n_up) == (j < s.n_up);
+            float q2 = 1.0f / fmaf(fabsf(cbs), d, 1.0f);
+            g_cb = fmaf(-(same ? s.cusp_same : s.cusp_diff) * d * d, q2 * q2, g_cb);
           }
         }
+        for (int a = 0; a < s.A; ++a) {
+          float dx = xi - s.R[3 * a], dy = yi - s.R[3 * a + 1], dz = zi - s.R[3 * a + 2];
+          float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          float q = 1.0f / fmaf(b_en, d, 1.0f);
+          g_aen = fmaf(d, q, g_aen);
+          g_ben = fmaf(-a_en * d * d, q * q, g_ben);
+        }
+      }
+      if (s.use_cusp) g_cb *= (cbs < 0.f ? -1.f : (cbs > 0.f ? 1.f : 0.f));
+      float v0 = warp_sum(wt * g_aee), v1 = warp_sum(wt * g_aen), v2 = warp_sum(wt * g_bee), v3 = warp_sum(wt * g_ben),
+            v4 = warp_sum(wt * g_cb);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sacc[0], v0); atomicAdd(&sacc[1], v1); atomicAdd(&sacc[2], v2); atomicAdd(&sacc[3], v3);
+        atomicAdd(&sacc[4], v4);
       }
     }
-    if (s.use_cusp) g_cb *= (cbs < 0.f ? -1.f : (cbs > 0.f ? 1.f : 0.f));
-    float v0 = warp_sum(wt * g_aee), v1 = warp_sum(wt * g_aen), v2 = warp_sum(wt * g_bee), v3 = warp_sum(wt * g_ben),
-          v4 = warp_sum(wt * g_cb);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&sacc[0], v0); atomicAdd(&sacc[1], v1); atomicAdd(&sacc[2], v2); atomicAdd(&sacc[3], v3);
-      atomicAdd(&sacc[4], v4);
+    if (s.use_cusp) {
+      // slots: 5 + a*81 + {b0[16], W0[3][16], b1, W1[16]} in *theta leaf order* of the nucleus
+      const float* W0 = theta + s.en_cusp_W0[an];
+      const float* b0 = theta + s.en_cusp_b0[an];
+      const float* W1 = theta + s.en_cusp_W1[an];
+      const int base = 5 + an * 81;
+      float swd = 0.f;
+      for (int i = 0; i < s.N; ++i) {                 // this thread's electron-nucleus distances, kept in shared memory
+        const float dx = r[(int64_t)(3 * i) * W + wc] - s.R[3 * an], dy = r[(int64_t)(3 * i + 1) * W + wc] - s.R[3 * an + 1],
+                    dz = r[(int64_t)(3 * i + 2) * W + wc] - s.R[3 * an + 2];
+        const float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        sd[i * WT + threadIdx.x] = d;
+        se[i * WT + threadIdx.x] = __expf(-d);
+        swd = fmaf(wt, d, swd);
+      }
+      const float sb1 = warp_sum(swd);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[base + 64], sb1);
+      for (int h = 0; h < NQMC_CUSP_H; ++h) {
+        const float w0 = W0[h], w1 = W0[NQMC_CUSP_H + h], w2 = W0[2 * NQMC_CUSP_H + h], bb = b0[h], wo = W1[h];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+        for (int i = 0; i < s.N; ++i) {
+          const float d = sd[i * WT + threadIdx.x], e = se[i * WT + threadIdx.x];
+          const float wd = wt * d;
+          const float t = nq_tanh(fmaf(w0, d, fmaf(w1, d * d, fmaf(w2, e, bb))));
+          const float dz_ = wd * wo * fmaf(-t, t, 1.0f);
+          a0 += dz_;
+          a1 = fmaf(dz_, d, a1);
+          a2 = fmaf(dz_ * d, d, a2);
+          a3 = fmaf(dz_, e, a3);
+          a4 = fmaf(wd, t, a4);
+        }
+        const float v0 = warp_sum(a0), v1 = warp_sum(a1), v2 = warp_sum(a2), v3 = warp_sum(a3), v4 = warp_sum(a4);
+        if ((threadIdx.x & 31) == 0) {
+          atomicAdd(&sacc[base + h], v0);
+          atomicAdd(&sacc[base + 16 + h], v1);
+          atomicAdd(&sacc[base + 32 + h], v2);
+          atomicAdd(&sacc[base + 48 + h], v3);
+          atomicAdd(&sacc[base + 65 + h], v4);
+        }
+      }
     }
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < n_slots; q += WT) part[(int64_t)blockIdx.x * n_slots + q] = (double)sacc[q];
+  const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int q = threadIdx.x; q < n_slots; q += WT) part[blk * n_slots + q] = (double)sacc[q];
 }
 
 __global__ void walker_grads_finish_kernel(const DevSys s, const double* __restrict__ part, const int nblk,
@@ -828,15 +854,16 @@ int nq_launch_walker_grads(nqmc_ctx* ctx, const float* r, const float* wgt, cons
                            int64_t W, double* out, cudaStream_t st) {
   const DevSys& s = ctx->sys;
   const int n_slots = 5 + (s.use_cusp ? 81 * s.A : 0);
+  const int ny = s.use_cusp ? s.A : 1;               // one block row per nucleus (e-n cusp networks)
   int nblk = (int)((W + WT - 1) / WT);
-  const int cap = (int)((int64_t)ctx->n_blk_walk * NPART / n_slots);
+  const int cap = (int)((int64_t)ctx->n_blk_walk * NPART / n_slots) / ny;
   if (nblk > cap) nblk = cap;
   if (nblk > 4 * ctx->sm_count) nblk = 4 * ctx->sm_count;
   if (nblk < 1) nblk = 1;
-  walker_grads_kernel<<<nblk, WT, n_slots * sizeof(float), st>>>(s, ctx->theta, r, wgt, hdr_center, e_l, W,
-                                                                 ctx->part_walk, n_slots);
+  const size_t smem = (((size_t)n_slots + 3) & ~(size_t)3) * sizeof(float) + (s.use_cusp ? 2 * NQMC_MAX_ELEC * WT * sizeof(float) : 0);
+  walker_grads_kernel<<<dim3(nblk, ny), WT, smem, st>>>(s, ctx->theta, r, wgt, hdr_center, e_l, W, ctx->part_walk, n_slots);
   NQMC_LAUNCH_CHECK();
-  walker_grads_finish_kernel<<<(n_slots * 32 + 127) / 128, 128, 0, st>>>(s, ctx->part_walk, nblk, n_slots, out);
+  walker_grads_finish_kernel<<<(n_slots * 32 + 127) / 128, 128, 0, st>>>(s, ctx->part_walk, nblk * ny, n_slots, out);
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }
