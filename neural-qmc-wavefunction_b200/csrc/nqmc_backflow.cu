@@ -432,7 +432,11 @@ __global__ void __launch_bounds__(WT) assemble_bf_kernel(const DevSys s, const f
 // weighted parameter gradient of the eta network:
 //   d log|det| / d eta_p = (v_i - v_j) . (r_i - r_j)   =>   rows = (walker, pair), a 2-16-16-1 reverse pass.
 // Phase 1: one thread per row computes h1, delta2, delta1 into shared memory.
-// Phase 2: thread (j,k) accumulates dW2[j][k] over the rows of the chunk; a few threads own the small leaves.
+// Phase 2: register-blocked: the 256 threads are 16 row groups x 16 threads; thread (g, b) owns the 4 x 4 block
+// (4 (b / 4), 4 (b % 4)) of dW2 and column b of the small leaves for rows g, g + 16, ... of the chunk -- two LDS.128
+// feed 16 FMAs (round 1: thread (j, k) took every row of the chunk with two scalar loads per FMA, and three warps walked
+// all rows again for the small leaves: 264 us at 32,768 walkers, H6).  The 16 groups are summed in shared memory once,
+// after the last chunk.
 constexpr int BT = 256;          // threads per CTA
 constexpr int BR = 128;          // rows per chunk (static shared memory stays under 48 KB)
 constexpr int BF_P = 2 * BH + BH + BH * BH + BH + BH + 1;   // 337
@@ -442,15 +446,24 @@ __global__ void __launch_bounds__(BT) bf_grads_kernel(const DevSys s, const floa
                                                       const float* __restrict__ wgt, const double* __restrict__ hdr,
                                                       const float* __restrict__ e_l, const int64_t W,
                                                       float* __restrict__ part) {
-  __shared__ float sh_h1[BR][BH + 1], sh_d2[BR][BH + 1], sh_d1[BR][BH + 1], sh_sh2[BR][BH + 1], sh_f[BR][2], sh_seed[BR];
+  constexpr int LD = BH + 4;       // row stride of the staging arrays: 16-byte aligned rows for the LDS.128 of phase 2
+  __shared__ __align__(16) float sh_h1[BR][LD], sh_d2[BR][LD], sh_d1[BR][LD], sh_sh2[BR][LD];
+  __shared__ float sh_f[BR][2], sh_seed[BR];
+  __shared__ float sh_red[BF_P];
   const MlpOff o = s.bf;
   const int tid = threadIdx.x;
   const int N = s.N, NP = N * (N - 1) / 2;
   const int64_t n_rows = W * NP;
   float center = 0.f;
   if (hdr) center = (float)(hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0));
-  float accW2 = 0.f, accS = 0.f;     // accS: role-dependent small-leaf accumulator
-  const int jrow = tid / BH, kcol = tid % BH;
+  const int grp = tid >> 4, b16 = tid & 15, jb = 4 * (b16 >> 2), kb = 4 * (b16 & 3);
+  float accW2[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accW2[a][c] = 0.f;
+  float a_b1 = 0.f, a_b2 = 0.f, a_w3 = 0.f, a_w10 = 0.f, a_w11 = 0.f, a_b3 = 0.f;   // small leaves, column b16
+  for (int q = tid; q < BF_P; q += BT) sh_red[q] = 0.f;
   for (int64_t row0 = (int64_t)blockIdx.x * BR; row0 < n_rows; row0 += (int64_t)gridDim.x * BR) {
     // ---- phase 1 -------------------------------------------------------------------------
     if (tid < BR) {
@@ -502,28 +515,40 @@ __global__ void __launch_bounds__(BT) bf_grads_kernel(const DevSys s, const floa
     }
     __syncthreads();
     // ---- phase 2 -------------------------------------------------------------------------
-    for (int rw = 0; rw < BR; ++rw) {
-      accW2 = fmaf(sh_h1[rw][jrow], sh_d2[rw][kcol], accW2);
-      // small leaves: tid 0..31 dW1[f][j], 32..47 db1, 48..63 db2, 64..79 dW3, 80 db3
-      float t = 0.f;
-      if (tid < 32) t = sh_f[rw][tid / BH] * sh_d1[rw][tid % BH];
-      else if (tid < 48) t = sh_d1[rw][tid - 32];
-      else if (tid < 64) t = sh_d2[rw][tid - 48];
-      else if (tid < 80) t = sh_sh2[rw][tid - 64];
-      else if (tid == 80) t = sh_seed[rw];
-      accS += t;
+#pragma unroll 2
+    for (int rw = grp; rw < BR; rw += BT / 16) {
+      const float4 hv = *reinterpret_cast<const float4*>(&sh_h1[rw][jb]);
+      const float4 dv = *reinterpret_cast<const float4*>(&sh_d2[rw][kb]);
+      const float h4[4] = {hv.x, hv.y, hv.z, hv.w}, d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) accW2[a][c] = fmaf(h4[a], d4[c], accW2[a][c]);
+      const float d1v = sh_d1[rw][b16];
+      a_b1 += d1v;
+      a_w10 = fmaf(sh_f[rw][0], d1v, a_w10);
+      a_w11 = fmaf(sh_f[rw][1], d1v, a_w11);
+      a_b2 += sh_d2[rw][b16];
+      a_w3 += sh_sh2[rw][b16];
+      if (b16 == 0) a_b3 += sh_seed[rw];
     }
     __syncthreads();
   }
-  // slab in theta-relative order of the backflow block: b1[16] W1[2][16] b2[16] W2[16][16] b3 W3[16]
-  float* slab = part + (int64_t)blockIdx.x * BF_P;
+  // sum the 16 row groups; slab in theta-relative order of the backflow block: b1[16] W1[2][16] b2[16] W2[16][16] b3 W3[16]
   const int o_b1 = 0, o_W1 = BH, o_b2 = 3 * BH, o_W2 = 4 * BH, o_b3 = 4 * BH + BH * BH, o_W3 = o_b3 + 1;
-  slab[o_W2 + jrow * BH + kcol] = accW2;
-  if (tid < 32) slab[o_W1 + tid] = accS;
-  else if (tid < 48) slab[o_b1 + tid - 32] = accS;
-  else if (tid < 64) slab[o_b2 + tid - 48] = accS;
-  else if (tid < 80) slab[o_W3 + tid - 64] = accS;
-  else if (tid == 80) slab[o_b3] = accS;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(&sh_red[o_W2 + (jb + a) * BH + kb + c], accW2[a][c]);
+  atomicAdd(&sh_red[o_b1 + b16], a_b1);
+  atomicAdd(&sh_red[o_W1 + b16], a_w10);
+  atomicAdd(&sh_red[o_W1 + BH + b16], a_w11);
+  atomicAdd(&sh_red[o_b2 + b16], a_b2);
+  atomicAdd(&sh_red[o_W3 + b16], a_w3);
+  if (b16 == 0) atomicAdd(&sh_red[o_b3], a_b3);
+  __syncthreads();
+  float* slab = part + (int64_t)blockIdx.x * BF_P;
+  for (int q = tid; q < BF_P; q += BT) slab[q] = sh_red[q];
 }
 
 __global__ void bf_grads_finish_kernel(const DevSys s, const float* __restrict__ part, const int nblk,
