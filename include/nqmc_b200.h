@@ -245,6 +245,15 @@ int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream
 int nqmc_sr_update(nqmc_ctx* ctx, float* Ot, const float* e_l, int64_t P, int64_t n, int64_t ld, float reg, float lr,
                    int32_t max_iter, double tol, float* S, double* work, double* delta, double* info, nqmc_stream stream);
 
+/* ---- debugging ------------------------------------------------------------------------------
+ * With NQMC_GUARD=1 in the environment when nqmc_reserve runs, every internal scratch buffer is allocated with a 4 KB
+ * guard band on either side.  nqmc_debug_check_guards synchronises the device and returns the number of buffers whose
+ * bands were overwritten (0: none; nqmc_last_error names them), or 0 when the guard mode is off. */
+int nqmc_debug_check_guards(nqmc_ctx* ctx);
+/* Guard mode only: device pointer of the named internal scratch buffer ("phi", "inv", "logabs", ...), else NULL.
+ * For tests of the checker itself. */
+void* nqmc_debug_scratch_ptr(nqmc_ctx* ctx, const char* name);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t nqmc_launch_count(const nqmc_ctx* ctx);

@@ -85,12 +85,38 @@ int check_w(nqmc_ctx* ctx, int64_t W) {
   return NQMC_OK;
 }
 
+// Scratch allocation.  With NQMC_GUARD=1 in the environment at nqmc_create every scratch buffer gets a 4 KB guard band on
+// either side, filled with a pattern that nqmc_debug_check_guards() verifies: the out-of-bounds check of this library
+// (compute-sanitizer is not available on the GPU pool this was developed on).
+constexpr size_t GUARD_BYTES = 4096;
+constexpr int GUARD_BYTE = 0xA5;
+cudaError_t scratch_alloc(nqmc_ctx* c, void** out, size_t bytes, const char* name) {
+  if (!c->guard) return cudaMalloc(out, bytes);
+  const size_t padded = (bytes + 255) / 256 * 256;
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), padded + 2 * GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, GUARD_BYTE, padded + 2 * GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  *out = base + GUARD_BYTES;
+  c->guards.push_back({base, bytes, padded, name});
+  return cudaSuccess;
+}
+void scratch_free(nqmc_ctx* c, void* p) {
+  if (!p) return;
+  if (c->guard) {
+    for (auto& g : c->guards)
+      if (g.base + GUARD_BYTES == p) { cudaFree(g.base); g.base = nullptr; return; }
+  }
+  cudaFree(p);
+}
+
 void free_scratch(nqmc_ctx* c) {
   void* ptrs[] = {c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
                   c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  for (void* p : ptrs) scratch_free(c, p);
+  c->guards.clear();
   c->x_cur = c->x_prop = c->vvec = c->gbf = nullptr;
   c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
@@ -251,46 +277,47 @@ int nqmc_destroy(nqmc_ctx* ctx) {
 
 int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   if (!ctx || W <= 0) return NQMC_ERR_ARG;
+  if (const char* e = getenv("NQMC_GUARD")) ctx->guard = atoi(e) != 0;
   NQMC_CUDA(cudaSetDevice(ctx->device));
   if (W <= ctx->cap_w) return NQMC_OK;
   free_scratch(ctx);
   const DevSys& s = ctx->sys;
   const size_t nn = 3 * (size_t)s.N, w = (size_t)W, f = sizeof(float);
   const size_t n_ent = s.n_ent > 0 ? s.n_ent : 1;
-  NQMC_CUDA(cudaMalloc(&ctx->r_prop, nn * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->phi, (s.use_bf ? 10 : 5) * n_ent * w * f));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->r_prop), nn * w * f, "r_prop"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->phi), (s.use_bf ? 10 : 5) * n_ent * w * f, "phi"));
   if (s.use_bf) {
-    NQMC_CUDA(cudaMalloc(&ctx->x_cur, nn * w * f));
-    NQMC_CUDA(cudaMalloc(&ctx->x_prop, nn * w * f));
-    NQMC_CUDA(cudaMalloc(&ctx->vvec, nn * w * f));
-    NQMC_CUDA(cudaMalloc(&ctx->gbf, 2 * nn * w * f));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->x_cur), nn * w * f, "x_cur"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->x_prop), nn * w * f, "x_prop"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->vvec), nn * w * f, "vvec"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->gbf), 2 * nn * w * f, "gbf"));
   }
-  NQMC_CUDA(cudaMalloc(&ctx->inv, n_ent * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->logabs, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->sign, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->e_scratch, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->wgt, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->r_soa, nn * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->nrm_soa, nn * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->aos_stage, nn * w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->uni_stage, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->logp_stage, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->nacc_stage, w * f));
-  NQMC_CUDA(cudaMalloc(&ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double)));
-  NQMC_CUDA(cudaMalloc(&ctx->hdr_tmp, NQMC_HDR_SIZE * sizeof(double)));
-  NQMC_CUDA(cudaMalloc(&ctx->jas_sums, 8 * sizeof(double)));
-  NQMC_CUDA(cudaMalloc(&ctx->gsum_stage, (size_t)s.P * sizeof(double)));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->inv), n_ent * w * f, "inv"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->logabs), w * f, "logabs"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->sign), w * f, "sign"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->e_scratch), w * f, "e_scratch"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->wgt), w * f, "wgt"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->r_soa), nn * w * f, "r_soa"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->nrm_soa), nn * w * f, "nrm_soa"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->aos_stage), nn * w * f, "aos_stage"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->uni_stage), w * f, "uni_stage"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->logp_stage), w * f, "logp_stage"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->nacc_stage), w * f, "nacc_stage"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->hdr_stage), NQMC_HDR_SIZE * sizeof(double), "hdr_stage"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->hdr_tmp), NQMC_HDR_SIZE * sizeof(double), "hdr_tmp"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->jas_sums), 8 * sizeof(double), "jas_sums"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->gsum_stage), (size_t)s.P * sizeof(double), "gsum_stage"));
   ctx->n_blk_walk = 65536;
-  NQMC_CUDA(cudaMalloc(&ctx->part_walk, (size_t)ctx->n_blk_walk * 16 * sizeof(double)));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->part_walk), (size_t)ctx->n_blk_walk * 16 * sizeof(double), "part_walk"));
   ctx->n_cta_bwd = 2 * ctx->sm_count;
-  NQMC_CUDA(cudaMalloc(&ctx->part_mlp, (size_t)ctx->n_cta_bwd * ctx->p_mlp * f));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->part_mlp), (size_t)ctx->n_cta_bwd * ctx->p_mlp * f, "part_mlp"));
   if (s.kind == NQMC_KIND_ANTISYMMETRIC && s.H == 128 && s.F + 1 <= 32) {
     ctx->bw_rows = nq_bwd128_rows(ctx, W);
     const size_t per = (size_t)s.n_mlp * 128 * (size_t)ctx->bw_rows * f;
-    NQMC_CUDA(cudaMalloc(&ctx->bw_h, per));
-    NQMC_CUDA(cudaMalloc(&ctx->bw_d, per));
-    NQMC_CUDA(cudaMalloc(&ctx->bw_e, per));
-    NQMC_CUDA(cudaMalloc(&ctx->bw_f, per / 4));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_h), per, "bw_h"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_d), per, "bw_d"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_e), per, "bw_e"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_f), per / 4, "bw_f"));
     NQMC_CUDA(cudaMemset(ctx->bw_f, 0, per / 4));       // feature rows F+1..31 stay zero
   }
   ctx->cap_w = W;
@@ -675,6 +702,37 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
   NQMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_done, 0));   // the next call on this stream reuses the staging buffers
   NQMC_CUDA(cudaStreamSynchronize(st));
   return NQMC_OK;
+}
+
+int nqmc_debug_check_guards(nqmc_ctx* ctx) {
+  if (!ctx) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaDeviceSynchronize());
+  if (!ctx->guard) return 0;
+  int bad = 0;
+  std::vector<unsigned char> host(GUARD_BYTES + 256);
+  ctx->err.clear();
+  for (const auto& g : ctx->guards) {
+    if (!g.base) continue;
+    bool hit = false;
+    NQMC_CUDA(cudaMemcpy(host.data(), g.base, GUARD_BYTES, cudaMemcpyDeviceToHost));               // band in front
+    for (size_t i = 0; i < GUARD_BYTES; ++i) hit |= host[i] != GUARD_BYTE;
+    const size_t tail = g.padded - g.bytes + GUARD_BYTES;                                           // slack + band behind
+    NQMC_CUDA(cudaMemcpy(host.data(), g.base + GUARD_BYTES + g.bytes, tail, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tail; ++i) hit |= host[i] != GUARD_BYTE;
+    if (hit) {
+      ++bad;
+      ctx->err += std::string(ctx->err.empty() ? "guard band overwritten: " : ", ") + g.name;
+    }
+  }
+  return bad;
+}
+
+void* nqmc_debug_scratch_ptr(nqmc_ctx* ctx, const char* name) {
+  if (!ctx || !name) return nullptr;
+  for (const auto& g : ctx->guards)
+    if (g.base && std::string(g.name) == name) return g.base + GUARD_BYTES;
+  return nullptr;
 }
 
 int64_t nqmc_launch_count(const nqmc_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -108,6 +108,10 @@ struct nqmc_ctx {
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
   const float* sigma_dev = nullptr;       // device-resident proposal width (set by nqmc_sample while it runs)
+  // NQMC_GUARD=1: guard bands around every scratch buffer (nqmc_debug_check_guards)
+  struct Guard { char* base; size_t bytes, padded; const char* name; };
+  bool guard = false;
+  std::vector<Guard> guards;
   bool theta_dirty = true;                // a theta writer was enqueued since the last PDL-attributed launch (see nq_launch_pdl)
   // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
   bool prof_on = false;

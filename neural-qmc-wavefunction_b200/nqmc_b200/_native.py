@@ -32,7 +32,7 @@ EXPORTS = [
     "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
     "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync", "nqmc_stream_wait",
-    "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update", "nqmc_log_psi_grads", "nqmc_apply_update",
+    "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update", "nqmc_log_psi_grads", "nqmc_apply_update", "nqmc_debug_check_guards", "nqmc_debug_scratch_ptr",
 ]
 
 
@@ -111,6 +111,9 @@ def load_library():
     lib.nqmc_sr_update.argtypes = [vp, vp, vp, i64, i64, i64, f32, f32, C.c_int32, C.c_double, vp, vp, vp, vp, vp]
     lib.nqmc_log_psi_grads.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.nqmc_apply_update.argtypes = [vp, vp, i64, vp]
+    lib.nqmc_debug_check_guards.argtypes = [vp]
+    lib.nqmc_debug_scratch_ptr.argtypes = [vp, C.c_char_p]
+    lib.nqmc_debug_scratch_ptr.restype = vp
     lib.nqmc_device_count.argtypes = []
     lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
     lib.nqmc_dev_free.argtypes = [C.c_int, vp]
@@ -645,6 +648,19 @@ class Context:
         self._check(self.lib.nqmc_sr_update(self.h, _ptr(Ot), _ptr(e_l), P, n, n, float(reg), float(lr), int(max_iter),
                                             float(tol), S.ptr, work.ptr, delta.ptr, info.ptr, self.stream), "nqmc_sr_update")
         return delta, info, S
+
+    def debug_scratch_ptr(self, name: str) -> int:
+        p = self.lib.nqmc_debug_scratch_ptr(self.h, name.encode())
+        if not p:
+            raise NativeError(f"no guarded scratch buffer named {name!r} (NQMC_GUARD=1 before the first call?)")
+        return int(p)
+
+    def check_guards(self) -> int:
+        """NQMC_GUARD=1 only: number of scratch buffers whose guard bands were overwritten (raises with their names)."""
+        n = int(self.lib.nqmc_debug_check_guards(self.h))
+        if n != 0:
+            self._check(-4 if n > 0 else n, "nqmc_debug_check_guards")
+        return n
 
     def rng_fill(self, W: int, seed: int, step: int, walker_id0: int = 0):
         n, u = self.empty((3 * self.n_elec, W)), self.empty(W)
