@@ -198,6 +198,34 @@ def sr_syrk_rate(ctx, peak3):
             "note": "algorithmic = n P (P+1) flops (upper triangle); executed = tiles touching it"}
 
 
+def sr_iteration_rate(iters=5):
+    """One full Stochastic-Reconfiguration VMC iteration through the drop-in API (VMCOptimizer(optimizer='sr')): config 1's
+    H2 SimpleWavefunction (64, 64), P = 4,673, 8,192 chains x 8 samples = 65,536 samples per iteration -- sampling, E_L,
+    per-walker O on the device, tcgen05 SYRK, CG solve, theta update."""
+    from nqmc_b200 import random as nqrandom
+    from nqmc_b200.optimizer import VMCOptimizer
+    from nqmc_b200.systems.molecule import hydrogen_molecule
+    from nqmc_b200.wavefunction import SimpleWavefunction
+    mol = hydrogen_molecule(1.4)
+    wf = SimpleWavefunction(hidden_dims=(64, 64), envelope_decay=1.0, nuclear_positions=mol.positions)
+    key = nqrandom.PRNGKey(SEED)
+    key, k0, k1 = nqrandom.split(key, 3)
+    params = wf.init(k0, np.zeros((2, 3)))
+    opt = VMCOptimizer(learning_rate=0.05, n_samples=8, n_chains=8192, n_burn=50, step_size=0.3, optimizer="sr",
+                       sr_regularization=1e-3, sr_max_iter=100, sr_tol=1e-5)
+    st = opt.init(k1, wf, params, mol)
+    for _ in range(2):
+        key, ks = nqrandom.split(key)
+        st, m = opt.step(ks, st, wf, mol)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        key, ks = nqrandom.split(key)
+        st, m = opt.step(ks, st, wf, mol)
+    dt = (time.perf_counter() - t0) / iters
+    return {"iterations_per_s": 1.0 / dt, "ms_per_iteration": dt * 1e3, "P": 4673, "samples_per_iteration": 65536,
+            "last_metrics": m, "timing": "host wall clock around VMCOptimizer.step"}
+
+
 def other_configs(flush, peak3, ffma_peak):
     """The BASELINE configs that are not the headline, on ONE GPU at their per-GPU sizes (configs[2] and [4] name 8
     GPUs: 262,144 / 8 and 1,048,576 / 8 walkers), same event timing and L2 flush as the headline."""
@@ -499,6 +527,10 @@ def run_ours(args):
                 out["sr_syrk"] = sr_syrk_rate(ctx, peak3)
             except Exception as e:      # report, do not hide
                 out["sr_syrk"] = {"error": repr(e)}
+            try:
+                out["sr_iteration"] = sr_iteration_rate()
+            except Exception as e:
+                out["sr_iteration"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_walkers, steps=2, warmup=1)
     if world > 1:
