@@ -114,7 +114,7 @@ void scratch_free(nqmc_ctx* c, void* p) {
 void free_scratch(nqmc_ctx* c) {
   void* ptrs[] = {c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
-                  c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f};
+                  c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f, c->l1cache};
   for (void* p : ptrs) scratch_free(c, p);
   c->guards.clear();
   c->x_cur = c->x_prop = c->vvec = c->gbf = nullptr;
@@ -124,6 +124,7 @@ void free_scratch(nqmc_ctx* c) {
   c->jas_valid_for = nullptr;
   c->part_mlp = nullptr;
   c->bw_h = c->bw_d = c->bw_e = c->bw_f = nullptr;
+  c->l1cache = nullptr;
   c->bw_rows = 0;
   c->cap_w = 0;
 }
@@ -311,6 +312,8 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->part_walk), (size_t)ctx->n_blk_walk * 16 * sizeof(double), "part_walk"));
   ctx->n_cta_bwd = 2 * ctx->sm_count;
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->part_mlp), (size_t)ctx->n_cta_bwd * ctx->p_mlp * f, "part_mlp"));
+  if (s.kind == NQMC_KIND_ANTISYMMETRIC && s.H == 128)
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->l1cache), (size_t)ctx->sm_count * 16 * 10 * 512 * f, "l1cache"));
   if (s.kind == NQMC_KIND_ANTISYMMETRIC && s.H == 128 && s.F + 1 <= 32) {
     ctx->bw_rows = nq_bwd128_rows(ctx, W);
     const size_t per = (size_t)s.n_mlp * 128 * (size_t)ctx->bw_rows * f;

@@ -104,6 +104,7 @@ struct nqmc_ctx {
   float* bw_e = nullptr;       // [n_mlp][128][bw_rows] delta1
   float* bw_f = nullptr;       // [n_mlp][32][bw_rows]  [1 | features]
   int64_t bw_rows = 0;
+  float* l1cache = nullptr;    // [sm_count][16 chunks][10][512] layer-1 outputs parked between the two output passes of the width-128 5-channel kernel
   double* hdr_tmp = nullptr;   // [8]
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)

@@ -120,7 +120,8 @@ struct BwdOut {
 template <int H, int NA, int CH, bool GW, int NBUF, bool BW>
 __global__ void __launch_bounds__(TCT, 1)
     orb_fwd_pc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
-                      float* __restrict__ phi, const int n_chunks, const float* __restrict__ Gw, const BwdOut bw) {
+                      float* __restrict__ phi, const int n_chunks, const float* __restrict__ Gw, const BwdOut bw,
+                      float* __restrict__ l1cache) {
   using C = Cfg<H, NA, CH, GW, NBUF, BW>;
   static_assert(!BW || (CH == 1 && !GW && !C::FEAT_SMEM && 3 + 2 * NA + 1 <= 32), "reverse-pass mode: value pass, <= 14 nuclei");
   constexpr int NT = C::NT, NPASS = C::NPASS, NCHUNK = C::NCHUNK, EPC = C::EPC;
@@ -322,14 +323,35 @@ __global__ void __launch_bounds__(TCT, 1)
       float2 out2[CH];                                         // even / odd columns of this thread, added at the end
 #pragma unroll
       for (int c = 0; c < CH; ++c) out2[c] = make_float2(0.f, 0.f);
+      float pre[(NPASS > 1) ? (CH == 1 ? 1 : 5) * UPT : 1];        // pass 1: the next chunk's cached layer-1 outputs
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass, ++ep) {
+        if (NPASS > 1 && pass > 0) {
+#pragma unroll
+          for (int q = 0; q < (CH == 1 ? 1 : 5) * UPT; ++q)
+            pre[q] = __ldcg(l1cache + (((int64_t)blockIdx.x * NCHUNK) * ((CH == 1 ? 1 : 5) * UPT) + q) * TCW + tid);
+        }
 #pragma unroll 2
         for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
           const int j0 = KC * kc + UPT * quarter;
           constexpr int CM = CH == 1 ? 1 : 5;                  // channels computed (CH = 4 exists for timing experiments only)
           float acc[CM][UPT];
-          {
+          // Two output passes (CH = 5, H = 128) need the same layer-1 / tanh-rule outputs twice.  They are computed in pass 0
+          // and parked in a per-CTA scratch that stays L2-resident (10 floats per thread and chunk, thread-major so each
+          // warp writes and reads 128 contiguous bytes; .cg on both sides: the lines are rewritten every tile); pass 1 loads
+          // them one chunk ahead instead of recomputing (-31 % of this kernel at 10 nuclei).
+          float* cslot = nullptr;
+          if constexpr (NPASS > 1) cslot = l1cache + (((int64_t)blockIdx.x * NCHUNK + kc) * (CM * UPT)) * TCW + tid;
+          if (NPASS > 1 && pass > 0) {
+#pragma unroll
+            for (int c = 0; c < CM; ++c)
+#pragma unroll
+              for (int u2 = 0; u2 < UPT; ++u2) acc[c][u2] = pre[c * UPT + u2];
+            if (kc + 1 < NCHUNK) {
+#pragma unroll
+              for (int q = 0; q < CM * UPT; ++q) pre[q] = __ldcg(cslot + (int64_t)(CM * UPT) * TCW + (int64_t)q * TCW);
+            }
+          } else {
             // the thread's two hidden units are one packed pair: every FMA / MUL / ADD below is one FFMA2 / FMUL2 / FADD2
             float2 pa[CM];
             pa[0] = *reinterpret_cast<const float2*>(b1s + j0);
@@ -390,6 +412,12 @@ __global__ void __launch_bounds__(TCT, 1)
             pa[0] = h;
 #pragma unroll
             for (int c = 0; c < CM; ++c) { acc[c][0] = pa[c].x; acc[c][1] = pa[c].y; }
+            if constexpr (NPASS > 1) {
+#pragma unroll
+              for (int c = 0; c < CM; ++c)
+#pragma unroll
+                for (int u2 = 0; u2 < UPT; ++u2) __stcg(cslot + (int64_t)(c * UPT + u2) * TCW, acc[c][u2]);
+            }
           }
           if constexpr (BW) {
             float* hr = bw.hT + ((int64_t)m * H + j0) * bw.rows_pad + rid;
@@ -518,6 +546,7 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* 
   const DevSys& s = ctx->sys;
   const size_t smem = C::smem_bytes(s.F);
   if (smem > 227 * 1024) return NQMC_ERR_UNSUPPORTED;
+  if (C::NPASS > 1 && ctx->l1cache == nullptr) return NQMC_ERR_UNSUPPORTED;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[ctx->device & 63];
   if (!configured) {
@@ -533,10 +562,10 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* 
   {
     ProfScope ps(ctx, BW ? NQ_PROF_BWD : (CH == 1 ? NQ_PROF_EVAL1 : NQ_PROF_EVAL5), st);
     if (ctx->prof_on)
-      orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, G, bw);
+      orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW><<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, G, bw, ctx->l1cache);
     else
       NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_fwd_pc_kernel<H, NA, CH, GW, NBUF, BW>, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s,
-                                      ctx->theta, r, W, phi, n_chunks, G, bw));
+                                      ctx->theta, r, W, phi, n_chunks, G, bw, ctx->l1cache));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
