@@ -37,7 +37,17 @@ struct Cfg {
   static constexpr int EPC = NT / NQ;                  // epilogue columns per thread
   static constexpr uint32_t C_A = CH * NT;             // first A-staging column
   static constexpr uint32_t A_LO = CH * KC, A_STRIDE = 2 * CH * KC;
-  static constexpr uint32_t TMEM_COLS = (C_A + NBUF * A_STRIDE) <= 256 ? 256 : 512;
+  // CH = 1 (value pass / reverse-pass value sweep): layer 1 on the tensor cores too.  The row's four threads write the
+  // features [x, y, z, 1, (d_a, exp(-d_a)) ...] as tf32 hi / lo straight into TMEM (nuclei dealt over the quarters), K1 / 8
+  // x 3 UMMAs with N = H form all pre-activations [f|1] [W1; b1] in 128 spare columns, and the chunk producer reads its
+  // two units with one tcgen05.ld instead of 2 (3 + 2 NA) FMAs behind as many weight loads (-1.0 of 3.0 ms at 10 nuclei).
+  static constexpr bool L1TC = CH == 1 && 4 + 2 * NA <= 24;
+  static constexpr int K1 = ((4 + 2 * NA + 7) / 8) * 8;
+  static constexpr uint32_t C_F1 = C_A + NBUF * A_STRIDE;        // features: K1 hi columns, then K1 lo columns
+  static constexpr uint32_t C_Z1 = 256;                          // pre-activations: H columns
+  static constexpr int W1B = (K1 / 4) * H * 16;                  // one [W1; b1] operand copy (hi or lo)
+  static constexpr uint32_t TMEM_COLS = L1TC ? 512 : ((C_A + NBUF * A_STRIDE) <= 256 ? 256 : 512);
+  static_assert(!L1TC || (C_F1 + 2 * K1 <= C_Z1 && C_Z1 + H <= 512), "TMEM: layer-1 operands do not fit");
   static_assert(C_A + NBUF * A_STRIDE <= 512, "TMEM: accumulators + A staging exceed 512 columns");
   // value pass: only d and exp(-d) per nucleus (2 NA registers); GW: one more value per nucleus + the six G entries
   static constexpr bool FEAT_SMEM = CH == 1 ? (NA > 16) : (NA > 6 || (GW && NA > 4));
@@ -46,8 +56,8 @@ struct Cfg {
   static constexpr uint32_t IDESC =
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
   static size_t smem_bytes(int F) {
-    return 2 * (size_t)B_MAT + ((size_t)F * H + 3 * H + (NQ - 1) * ROWS * CH) * 4 +
-           (FEAT_SMEM ? (size_t)NA * 2 * ROWS * 16 : 0) + 128;
+    return 2 * (size_t)B_MAT + (L1TC ? 2 * (size_t)W1B : 0) + ((size_t)F * H + 3 * H + (NQ - 1) * ROWS * CH) * 4 +
+           (FEAT_SMEM ? (size_t)NA * 2 * ROWS * 16 : 0) + 160;
   }
 };
 
@@ -128,7 +138,9 @@ __global__ void __launch_bounds__(TCT, 1)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* Bhi = smem_raw;                                    // [H/4][H n][4]
   uint8_t* Blo = Bhi + C::B_MAT;
-  float* W1s = reinterpret_cast<float*>(Blo + C::B_MAT);      // [F][H]
+  uint8_t* W1hi = Blo + C::B_MAT;                             // L1TC: [K1/4][H n][4] = [W1; b1]^T operand, hi / lo
+  uint8_t* W1lo = W1hi + (C::L1TC ? C::W1B : 0);
+  float* W1s = reinterpret_cast<float*>(W1lo + (C::L1TC ? C::W1B : 0));      // [F][H]
   float* b1s = W1s + s.F * H;
   float* b2s = b1s + H;
   float* W3s = b2s + H;
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(TCT, 1)
   float4* featA = reinterpret_cast<float4*>(outS + (NQ - 1) * ROWS * CH);   // [NA][ROWS] {d, e, 2/d, -}   (FEAT_SMEM)
   float4* featB = featA + (C::FEAT_SMEM ? NA * ROWS : 0);                   // [NA][ROWS] {ux, uy, uz, -}
   uint64_t* bars = reinterpret_cast<uint64_t*>(featB + (C::FEAT_SMEM ? NA * ROWS : 0));   // full[NBUF], empty[NBUF], dfull, dempty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 4);   // + f_full, z_full (L1TC)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (ROWS - 1), quarter = (tid >> 7) & (NQ - 1);
@@ -163,8 +175,24 @@ __global__ void __launch_bounds__(TCT, 1)
     reinterpret_cast<uint32_t*>(Bhi)[o] = hi;
     reinterpret_cast<uint32_t*>(Blo)[o] = lo;
   }
+  if constexpr (C::L1TC) {
+    for (int idx = tid; idx < C::K1 * H; idx += TCT) {
+      const int k = idx / H, n = idx % H;   // operand feature order: x, y, z, 1, then (d_a, exp(-d_a)) pairs, zero padding
+      float v = 0.f;
+      if (k < 3) v = theta[off.W1 + k * H + n];
+      else if (k == 3) v = theta[off.b1 + n];
+      else if (k < 4 + 2 * NA) v = theta[off.W1 + (((k - 4) & 1) ? 3 + NA + ((k - 4) >> 1) : 3 + ((k - 4) >> 1)) * H + n];
+      uint32_t hi, lo;
+      split_tf32(v, hi, lo);
+      const int o = (k >> 2) * (H * 4) + n * 4 + (k & 3);
+      reinterpret_cast<uint32_t*>(W1hi)[o] = hi;
+      reinterpret_cast<uint32_t*>(W1lo)[o] = lo;
+    }
+  }
   const float b3 = theta[off.b3];
   if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[2 * NBUF + 2])), "r"(NWW));   // f_full
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[2 * NBUF + 3])));              // z_full
     for (int b = 0; b < NBUF; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[b])), "r"(NWW));   // full[b]
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[NBUF + b])), "r"(NISS));   // empty[b]
@@ -186,6 +214,7 @@ __global__ void __launch_bounds__(TCT, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NBUF]);
   const uint32_t dfull = smem_u32(&bars[2 * NBUF]), dempty = smem_u32(&bars[2 * NBUF + 1]);
+  const uint32_t f_full = smem_u32(&bars[2 * NBUF + 2]), z_full = smem_u32(&bars[2 * NBUF + 3]);
 
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
@@ -198,7 +227,24 @@ __global__ void __launch_bounds__(TCT, 1)
     const uint32_t leader = elect_one();
     const uint64_t dBh = umma_desc(smem_u32(Bhi), C::B_K4, 128), dBl = umma_desc(smem_u32(Blo), C::B_K4, 128);
     uint32_t g = 0, ep = 0;                                    // global chunk counter, global pass counter
-    for (int64_t item = chunk; item < n_items; item += n_chunks) {
+    uint32_t tl = 0;                                           // local tile counter
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++tl) {
+      if constexpr (C::L1TC) {
+        if (iw == 0) {                                         // Z1 = [f|1] [W1; b1]: every worker has read Z1 of the previous tile
+          mbar_wait(f_full, tl & 1);                           // (they arrive here only after their chunk loop)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t d1h = umma_desc(smem_u32(W1hi), C::B_K4, 128), d1l = umma_desc(smem_u32(W1lo), C::B_K4, 128);
+#pragma unroll
+          for (int ks = 0; ks < C::K1 / 8; ++ks) {
+            const uint64_t kb = (uint64_t)(((uint32_t)ks * 2 * C::B_K4) >> 4);
+            const uint32_t ah = tmem_base + C::C_F1 + 8u * ks, al = ah + (uint32_t)C::K1;
+            umma_ts(tmem_base + C::C_Z1, ah, d1h + kb, C::IDESC, ks == 0 ? 0u : 1u, leader);
+            umma_ts(tmem_base + C::C_Z1, al, d1h + kb, C::IDESC, 1u, leader);
+            umma_ts(tmem_base + C::C_Z1, ah, d1l + kb, C::IDESC, 1u, leader);
+          }
+          umma_commit(z_full, leader);
+        }
+      }
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass, ++ep) {
         if (ep > 0) mbar_wait(dempty, (ep - 1) & 1);           // accumulators of the previous pass have been read
@@ -227,7 +273,17 @@ __global__ void __launch_bounds__(TCT, 1)
     // =============================== worker warps ========================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t g = 0, ep = 0;
+    uint32_t g = 0, ep = 0, tl = 0;
+    if constexpr (C::L1TC) {                                   // the padding feature columns must read as zero (written once)
+      if (quarter == NQ - 1) {
+#pragma unroll
+        for (int k = 4 + 2 * NA; k < C::K1; ++k) {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + lane_base + C::C_F1 + (uint32_t)k), "r"(0u) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + lane_base + C::C_F1 + (uint32_t)(C::K1 + k)), "r"(0u) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+    }
     float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
     float nwt = 1.f, ninv = 0.f;                               // BW: weight and inverse-matrix entry of the row
     float centerf = 0.f;
@@ -251,7 +307,7 @@ __global__ void __launch_bounds__(TCT, 1)
       }
     };
     if (chunk < n_items) fetch(chunk);
-    for (int64_t item = chunk; item < n_items; item += n_chunks) {
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++tl) {
       const int i = (int)(item % ns);
       const int64_t w0 = (item / ns) * ROWS;
       const float x = nx, y = ny, z = nz;
@@ -282,7 +338,50 @@ __global__ void __launch_bounds__(TCT, 1)
                2.0f * fmaf(g6[1] * a, b, fmaf(g6[2] * a, c, g6[4] * b * c));
       };
       const float trG = g6[0] + g6[3] + g6[5];
-      if constexpr (C::FEAT_SMEM) {
+      if constexpr (C::L1TC) {
+        // this thread's share of the row's features -> TMEM (and, in reverse-pass mode, -> fT); then Z1 from the issuer
+        const uint32_t fa = tmem_base + lane_base + C::C_F1;
+        float* fr = nullptr;
+        if constexpr (BW) fr = bw.fT + (int64_t)m * 32 * bw.rows_pad + rid;
+        if (quarter == 0) {
+          uint32_t h0, l0, h1, l1, h2, l2;
+          split_tf32(x, h0, l0);
+          split_tf32(y, h1, l1);
+          split_tf32(z, h2, l2);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(fa), "r"(h0), "r"(h1), "r"(h2), "r"(0x3f800000u) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(fa + (uint32_t)C::K1), "r"(l0), "r"(l1), "r"(l2), "r"(0u) : "memory");
+          if constexpr (BW) {
+            fr[0] = 1.0f;
+            fr[bw.rows_pad] = x;
+            fr[2 * bw.rows_pad] = y;
+            fr[3 * bw.rows_pad] = z;
+          }
+        }
+#pragma unroll
+        for (int a0 = 0; a0 < NA; a0 += NQ) {
+          const int a = a0 + quarter;
+          if (a < NA) {
+            const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
+            const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            const float ex = __expf(-dd);
+            uint32_t hd, ld, he, le;
+            split_tf32(dd, hd, ld);
+            split_tf32(ex, he, le);
+            tmem_st2(fa + (uint32_t)(4 + 2 * a), hd, he);
+            tmem_st2(fa + (uint32_t)(C::K1 + 4 + 2 * a), ld, le);
+            if constexpr (BW) {
+              fr[(int64_t)(4 + a) * bw.rows_pad] = dd;
+              fr[(int64_t)(4 + NA + a) * bw.rows_pad] = ex;
+            }
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(f_full);
+        mbar_wait(z_full, tl & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      } else if constexpr (C::FEAT_SMEM) {
         // every reader of the previous tile's table has passed that tile's quarter-combine barrier
         for (int a = quarter; a < NA; a += NQ) {
           const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
@@ -307,7 +406,7 @@ __global__ void __launch_bounds__(TCT, 1)
           }
         }
       }
-      if constexpr (BW) {                                        // [1 | x y z | d_a | e_a] of this row, dealt over its four threads
+      if constexpr (BW && !C::L1TC) {                            // [1 | x y z | d_a | e_a] of this row, dealt over its four threads
         float* fr = bw.fT + (int64_t)m * 32 * bw.rows_pad + rid;
         const float fv[4] = {1.0f, x, y, z};
 #pragma unroll
@@ -342,7 +441,13 @@ __global__ void __launch_bounds__(TCT, 1)
           // them one chunk ahead instead of recomputing (-31 % of this kernel at 10 nuclei).
           float* cslot = nullptr;
           if constexpr (NPASS > 1) cslot = l1cache + (((int64_t)blockIdx.x * NCHUNK + kc) * (CM * UPT)) * TCW + tid;
-          if (NPASS > 1 && pass > 0) {
+          if constexpr (C::L1TC) {
+            uint32_t z0, z1;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(z0), "=r"(z1) : "r"(tmem_base + lane_base + C::C_Z1 + (uint32_t)j0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float2 h = nq_tanh2(make_float2(__uint_as_float(z0), __uint_as_float(z1)));
+            acc[0][0] = h.x; acc[0][1] = h.y;
+          } else if (NPASS > 1 && pass > 0) {
 #pragma unroll
             for (int c = 0; c < CM; ++c)
 #pragma unroll
