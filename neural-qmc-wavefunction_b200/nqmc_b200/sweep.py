@@ -78,6 +78,23 @@ class GeometrySweep:
             for i, st in enumerate(self.states):
                 st.ctx.stream = self.side[i % len(self.side)]
 
+    def close(self):
+        """Destroy the side streams (the contexts go back to the caller's stream)."""
+        if self.side and self.states:
+            self.synchronize()
+            c = self.states[0].ctx
+            for st in self.states:
+                st.ctx.stream = self.main
+            for s_ in self.side:
+                c.lib.nqmc_stream_destroy(c.device, s_)
+            self.side = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def _fork(self):
         if self.side:
             c = self.states[0].ctx
