@@ -112,12 +112,12 @@ void scratch_free(nqmc_ctx* c, void* p) {
 }
 
 void free_scratch(nqmc_ctx* c) {
-  void* ptrs[] = {c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
+  void* ptrs[] = {c->bfw, c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
                   c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f, c->l1cache};
   for (void* p : ptrs) scratch_free(c, p);
   c->guards.clear();
-  c->x_cur = c->x_prop = c->vvec = c->gbf = nullptr;
+  c->x_cur = c->x_prop = c->vvec = c->gbf = c->bfw = nullptr;
   c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
@@ -292,6 +292,7 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->x_prop), nn * w * f, "x_prop"));
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->vvec), nn * w * f, "vvec"));
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->gbf), 2 * nn * w * f, "gbf"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bfw), nq_backflow_ws_floats(s) * w * f, "bfw"));
   }
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->inv), n_ent * w * f, "inv"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->logabs), w * f, "logabs"));
@@ -516,7 +517,7 @@ static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, flo
       if (rc == NQMC_OK) return nq_launch_assemble_bf(ctx, r, W, e_l, parts, 1, st);
       if (rc != NQMC_ERR_UNSUPPORTED) return rc;
     }
-    int rc = nq_launch_backflow_x(ctx, r, W, ctx->x_cur, st);
+    int rc = nq_launch_backflow_xg(ctx, r, W, ctx->x_cur, ctx->gbf, st);
     if (rc) return rc;
     rc = nq_launch_orb_eval(ctx, ctx->x_cur, W, 10, ctx->phi, st);      // FP32 FFMA: value, gradient, Hessian
     if (rc) return rc;

@@ -85,6 +85,7 @@ struct nqmc_ctx {
   float* x_prop = nullptr;     // [3N][cap_w] backflow coordinates of the proposal
   float* vvec = nullptr;       // [3N][cap_w] v_i = sum_k inv[k,i] grad phi_k(x_i)  (backflow reverse pass)
   float* gbf = nullptr;        // [6N][cap_w] G_i = sum_mu d_mu x_i d_mu x_i^T (weights of the backflow Laplacian channel)
+  float* bfw = nullptr;        // [nq_backflow_ws_floats][cap_w] eta table, Lap x, A, Q and partial sums (nqmc_backflow.cu)
   float* r_soa = nullptr;      // [3N][cap_w]  (host-entry staging)
   float* nrm_soa = nullptr;    // [3N][cap_w]
   float* aos_stage = nullptr;  // [cap_w][N][3]
@@ -319,6 +320,7 @@ int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
                      float* n_acc, cudaStream_t st);
 int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);
 int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st);
+size_t nq_backflow_ws_floats(const DevSys& s);
 int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cudaStream_t st);
 int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, int gw, cudaStream_t st);
 int nq_launch_backflow_xg(nqmc_ctx* ctx, const float* r, int64_t W, float* x, float* G, cudaStream_t st);
