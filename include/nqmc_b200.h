@@ -237,8 +237,10 @@ int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t 
 int64_t nqmc_sr_workspace_bytes(int64_t P);
 /* Per-walker log-derivatives, parameter-major: Ot[p * ld + w] = d log|psi(r_w)| / d theta_p, ld >= W.
  * Replaces: vmap(jax.grad(lambda p: wavefunction(p, r)))(samples) -- src/nqmc/optimizer/vmc.py:120-123 -- in the one
- * case where the matrix is wanted itself (the O of Stochastic Reconfiguration).  SimpleWavefunction only
- * (NQMC_ERR_UNSUPPORTED otherwise: the antisymmetric ansatz has 2e4..2e5 parameters, S would be 1.6 .. 160 GB). */
+ * case where the matrix is wanted itself (the O of Stochastic Reconfiguration).  Every ansatz: SimpleWavefunction
+ * (nqmc_simple.cu) and the antisymmetric one with or without cusps / backflow (nqmc_pergrad.cu; NQMC_ERR_UNSUPPORTED only
+ * when electrons-per-spin x hidden width exceed its shared-memory staging, e.g. H10 at width 128 -- whose S would be
+ * 155 GB anyway).  Ot: [P][ld], ld >= W; W <= the reserved walker count.  H4 / 64-wide, 65,536 samples: 5.2 GB in 5.3 ms. */
 int nqmc_log_psi_grads(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, nqmc_stream stream);
 /* theta += delta (fp64 update direction from nqmc_sr_update) in the ctx, on the device. */
 int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream stream);

@@ -570,6 +570,25 @@ int nqmc_grad_accum(nqmc_ctx* ctx, const float* r, const float* weight, int64_t 
   return grads_core(ctx, r, weight, nullptr, nullptr, W, out, S(st));
 }
 
+// O[p][w] = d log|psi(r_w)| / d theta_p for every walker (the O of Stochastic Reconfiguration)
+int nqmc_log_psi_grads(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, nqmc_stream st) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r || !Ot || ld < W) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_grads_per_walker(ctx, r, W, Ot, ld, S(st));
+  if (ctx->sys.use_bf) {
+    rc = energy_core(ctx, r, W, nullptr, nullptr, S(st));      // fills x_cur, inv and v
+    if (rc) return rc;
+  } else {
+    rc = nq_launch_orb_eval(ctx, r, W, 1, ctx->phi, S(st));
+    if (rc) return rc;
+    rc = nq_launch_assemble_inv(ctx, r, W, S(st));
+    if (rc) return rc;
+  }
+  return nq_antisym_grads_per_walker(ctx, r, W, Ot, ld, S(st));
+}
+
 int nqmc_energy_stats(nqmc_ctx* ctx, const float* e_l, int64_t W, double* hdr, nqmc_stream st) {
   int rc = check_w(ctx, W);
   if (rc) return rc;

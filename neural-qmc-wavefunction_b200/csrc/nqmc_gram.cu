@@ -447,17 +447,6 @@ int nqmc_gram(nqmc_ctx* ctx, const float* A, const float* B, int64_t M, int64_t 
   return launch_gram(ctx, A, B, M, N, K, lda, ldb, alpha, diag, symmetric, C, ldc, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int nqmc_log_psi_grads(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, nqmc_stream stream) {
-  if (!ctx || !r || !Ot || W <= 0 || ld < W) return NQMC_ERR_ARG;
-  NQMC_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->sys.kind != NQMC_KIND_SIMPLE) {
-    ctx->err = "nqmc_log_psi_grads: per-walker log-derivatives are materialised for SimpleWavefunction only (the antisymmetric "
-               "ansatz has 2e4..2e5 parameters: its S matrix would not fit; use nqmc_grad_accum)";
-    return NQMC_ERR_UNSUPPORTED;
-  }
-  return nq_simple_grads_per_walker(ctx, r, W, Ot, ld, reinterpret_cast<cudaStream_t>(stream));
-}
-
 int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream stream) {
   if (!ctx || !delta || P != ctx->sys.P) return NQMC_ERR_ARG;
   NQMC_CUDA(cudaSetDevice(ctx->device));

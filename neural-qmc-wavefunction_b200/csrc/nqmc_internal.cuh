@@ -321,6 +321,7 @@ int nq_accept_logabs(nqmc_ctx* ctx, float* r, float* logp, const float* r_prop, 
 int nq_launch_assemble_inv(nqmc_ctx* ctx, const float* r, int64_t W, cudaStream_t st);
 int nq_ffma_peak(nqmc_ctx* ctx, int reps, double* tflops, cudaStream_t st);
 size_t nq_backflow_ws_floats(const DevSys& s);
+int nq_antisym_grads_per_walker(nqmc_ctx* ctx, const float* r, int64_t W, float* Ot, int64_t ld, cudaStream_t st);
 int nq_launch_backflow_x(nqmc_ctx* ctx, const float* r, int64_t W, float* x, cudaStream_t st);
 int nq_launch_assemble_bf(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, int gw, cudaStream_t st);
 int nq_launch_backflow_xg(nqmc_ctx* ctx, const float* r, int64_t W, float* x, float* G, cudaStream_t st);

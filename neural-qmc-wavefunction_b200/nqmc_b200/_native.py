@@ -625,7 +625,7 @@ class Context:
         return out
 
     def log_psi_grads(self, r_soa) -> DeviceArray:
-        """Per-walker log-derivatives, parameter-major [P][W] (nqmc_log_psi_grads; SimpleWavefunction only)."""
+        """Per-walker log-derivatives, parameter-major [P][W] (nqmc_log_psi_grads; every ansatz)."""
         W = _shape(r_soa)[1]
         if W % 4:
             raise ValueError("log_psi_grads: the walker count must be a multiple of 4 (TMA row pitch of the SR kernels)")

@@ -125,7 +125,8 @@ class VMCOptimizer:
     target_acceptance: float = 0.5
     optimizer: str = "adam"         # "adam" (the reference's optax chain) or "sr": Stochastic Reconfiguration on the device
                                     # ([SPEC] .github/phase6-issue-body.md:130-182; nqmc_log_psi_grads + nqmc_sr_update),
-                                    # SimpleWavefunction; over ranks with the peer-memory communicator attached; learning_rate is the SR step, clip_grad unused
+                                    # any wavefunction whose P x P matrix fits; over ranks with the peer-memory communicator attached;
+                                    # learning_rate is the SR step, clip_grad unused
     sr_regularization: float = 1e-3
     sr_max_iter: int = 300
     sr_tol: float = 1e-6

@@ -273,3 +273,46 @@ def test_per_walker_log_derivatives_match_grad_accum_and_oracle():
     wgt = np.random.default_rng(0).standard_normal(64).astype(np.float32)
     g = ctx.grad_accum(soa, ctx.upload(wgt)).numpy(ctx.stream)
     assert np.allclose(g, Ot.astype(np.float64) @ wgt.astype(np.float64), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", [
+    dict(n_atoms=2, hidden=32), dict(n_atoms=4, hidden=64, use_cusp=True), dict(n_atoms=6, hidden=128, use_cusp=True),
+    dict(n_atoms=4, hidden=32, use_cusp=True, use_backflow=True), dict(n_atoms=6, hidden=64, use_backflow=True),
+], ids=lambda c: "H%d-h%d%s%s" % (c["n_atoms"], c["hidden"], "-cusp" if c.get("use_cusp") else "", "-bf" if c.get("use_backflow") else ""))
+def test_per_walker_log_derivatives_antisymmetric(case):
+    """nqmc_log_psi_grads for the Slater-Jastrow(-cusp, -backflow) ansatz: every column of O against the fp64 oracle, and
+    O^T w against the tensor-core weighted-sum kernels of the walker step (nqmc_grad_accum)."""
+    from _util import make_case, make_context, make_oracle
+    W = 100                                                            # ragged: not a multiple of the 32-walker tile
+    s, net, theta, r = make_case(W=W, burn=10, **case)
+    ctx = make_context(s, net)
+    ctx.set_params(theta)
+    soa = ctx.to_soa(r)
+    Ot = ctx.log_psi_grads(soa).numpy(ctx.stream)                      # [P][W]
+    assert Ot.shape == (ctx.P, W) and np.all(np.isfinite(Ot))
+    O = make_oracle(s, net).grad_log_psi(theta.astype(np.float64), r.astype(np.float64))   # [W][P]
+    col = np.maximum(np.max(np.abs(O), axis=0, keepdims=True), 1e-3)   # per-parameter scale
+    err = np.abs(Ot.T - O) / col
+    assert np.median(err) <= 1e-5 and np.quantile(err, 0.999) <= 2e-3, (np.median(err), np.quantile(err, 0.999), err.max())
+    wgt = np.random.default_rng(0).standard_normal(W).astype(np.float32)
+    g = ctx.grad_accum(soa, ctx.upload(wgt)).numpy(ctx.stream)
+    ref = Ot.astype(np.float64) @ wgt.astype(np.float64)
+    assert np.max(np.abs(g - ref)) <= 2e-4 * max(1.0, np.max(np.abs(ref))), np.max(np.abs(g - ref))
+
+
+def test_h2_slater_jastrow_vmc_with_stochastic_reconfiguration():
+    """optimizer='sr' with the antisymmetric ansatz (P = 1,558): per-walker O from nqmc_pergrad.cu, SYRK, CG, update."""
+    import nqmc_b200 as nqmc
+    from nqmc_b200.optimizer import VMCOptimizer
+    from nqmc_b200.systems.molecule import hydrogen_molecule
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction
+    mol = hydrogen_molecule(1.4)
+    wf = AntisymmetricWavefunction(1, 1, (32, 32), use_cusp=True, molecule=mol)
+    params = wf.init(nqmc.random.PRNGKey(0))
+    opt = VMCOptimizer(learning_rate=0.05, n_samples=8, n_chains=512, n_burn=200, step_size=0.3, optimizer="sr",
+                       sr_regularization=1e-3)
+    params, history = opt.train(nqmc.random.PRNGKey(1), wf, params, mol, n_steps=40, log_every=1000)
+    e = np.array([h["energy"] for h in history])
+    assert np.all(np.isfinite(e))
+    assert float(np.mean(e[-8:])) < float(np.mean(e[:4])) - 0.05, (e[:4], e[-8:])
+    assert -1.25 < float(np.mean(e[-8:])) < -1.05, e[-8:]
