@@ -226,6 +226,32 @@ def sr_iteration_rate(iters=5):
             "last_metrics": m, "timing": "host wall clock around VMCOptimizer.step"}
 
 
+def sr_iteration_rate_h4(iters=3):
+    """The same for the benchmark wavefunction (H4, four 11-64-64-1 orbital networks, P = 19,976): 8,192 chains x 8 samples =
+    65,536 samples per iteration; per-walker O from nqmc_pergrad.cu (5.2 GB), S = 1.6 GB."""
+    from nqmc_b200 import random as nqrandom
+    from nqmc_b200.optimizer import VMCOptimizer
+    from nqmc_b200.systems.molecule import hydrogen_chain
+    from nqmc_b200.wavefunction import AntisymmetricWavefunction
+    mol = hydrogen_chain(4, 1.8)
+    wf = AntisymmetricWavefunction(2, 2, (64, 64), molecule=mol)
+    key = nqrandom.PRNGKey(SEED)
+    key, k0, k1 = nqrandom.split(key, 3)
+    params = wf.init(k0)
+    opt = VMCOptimizer(learning_rate=0.05, n_samples=8, n_chains=8192, n_burn=50, step_size=0.5, optimizer="sr",
+                       sr_regularization=1e-3, sr_max_iter=100, sr_tol=1e-5)
+    st = opt.init(k1, wf, params, mol)
+    key, ks = nqrandom.split(key)
+    st, m = opt.step(ks, st, wf, mol)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        key, ks = nqrandom.split(key)
+        st, m = opt.step(ks, st, wf, mol)
+    dt = (time.perf_counter() - t0) / iters
+    return {"iterations_per_s": 1.0 / dt, "ms_per_iteration": dt * 1e3, "P": 19976, "samples_per_iteration": 65536,
+            "last_metrics": m, "timing": "host wall clock around VMCOptimizer.step"}
+
+
 def other_configs(flush, peak3, ffma_peak):
     """The BASELINE configs that are not the headline, on ONE GPU at their per-GPU sizes (configs[2] and [4] name 8
     GPUs: 262,144 / 8 and 1,048,576 / 8 walkers), same event timing and L2 flush as the headline."""
@@ -531,6 +557,10 @@ def run_ours(args):
                 out["sr_iteration"] = sr_iteration_rate()
             except Exception as e:
                 out["sr_iteration"] = {"error": repr(e)}
+            try:
+                out["sr_iteration_h4"] = sr_iteration_rate_h4()
+            except Exception as e:
+                out["sr_iteration_h4"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_walkers, steps=2, warmup=1)
     if world > 1:

@@ -8,7 +8,7 @@
 //     d_mu Phi[i,k]  = g_ik . d_mu x_i
 //     sum_mu d2_mu Phi[i,k] = sum_ab Hess_ik[ab] G_i[ab] + g_ik . Lap x_i,   G_i = sum_mu d_mu x_i d_mu x_i^T
 // Round 2: the orbital pass no longer needs the six Hessian channels.  Only the contraction sum_ab Hess_ik[ab] G_i[ab]
-// enters E_L, and G_i depends on the backflow Jacobian alone, so backflow_xg_kernel computes G_i BEFORE the orbital
+// enters E_L, and G_i depends on the backflow Jacobian alone, so backflow_elec_kernel computes G_i BEFORE the orbital
 // pass and the orbital kernels propagate the G-weighted Laplacian L_G = sum_ab G_ab d_a d_b forward instead -- it obeys
 // the same layer rules as the ordinary Laplacian (linear: L_G(W^T h) = W^T L_G(h); tanh: t' L_G(u) + t'' grad u^T G grad u)
 // -- i.e. 5 channels (value, gradient, L_G) instead of 10: half the flops, and the 5-channel tensor-core kernels apply.
