@@ -114,7 +114,7 @@ void scratch_free(nqmc_ctx* c, void* p) {
 void free_scratch(nqmc_ctx* c) {
   void* ptrs[] = {c->bfw, c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
-                  c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f, c->l1cache};
+                  c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f, c->bw_h2, c->l1cache};
   for (void* p : ptrs) scratch_free(c, p);
   c->guards.clear();
   c->x_cur = c->x_prop = c->vvec = c->gbf = c->bfw = nullptr;
@@ -123,7 +123,8 @@ void free_scratch(nqmc_ctx* c) {
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
   c->jas_valid_for = nullptr;
   c->part_mlp = nullptr;
-  c->bw_h = c->bw_d = c->bw_e = c->bw_f = nullptr;
+  c->bw_h = c->bw_d = c->bw_e = c->bw_f = c->bw_h2 = nullptr;
+  c->act_valid_for = nullptr;
   c->l1cache = nullptr;
   c->bw_rows = 0;
   c->cap_w = 0;
@@ -321,6 +322,7 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_h), per, "bw_h"));
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_d), per, "bw_d"));
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_e), per, "bw_e"));
+    NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_h2), per, "bw_h2"));
     NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->bw_f), per / 4, "bw_f"));
     NQMC_CUDA(cudaMemset(ctx->bw_f, 0, per / 4));       // feature rows F+1..31 stay zero
   }
@@ -354,6 +356,7 @@ int nqmc_set_params(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stream st
   }
   NQMC_CUDA(cudaSetDevice(ctx->device));
   ctx->theta_dirty = true;
+  ctx->act_valid_for = nullptr;
   NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyDeviceToDevice, S(st)));
   return NQMC_OK;
 }
@@ -366,6 +369,7 @@ int nqmc_set_params_host(nqmc_ctx* ctx, const float* theta, int64_t P, nqmc_stre
   }
   NQMC_CUDA(cudaSetDevice(ctx->device));
   ctx->theta_dirty = true;
+  ctx->act_valid_for = nullptr;
   NQMC_CUDA(cudaMemcpyAsync(ctx->theta, theta, sizeof(float) * (size_t)P, cudaMemcpyHostToDevice, S(st)));
   NQMC_CUDA(cudaStreamSynchronize(S(st)));
   return NQMC_OK;
@@ -507,6 +511,8 @@ int nqmc_sample(nqmc_ctx* ctx, float* r, float* logp, const float* normals, cons
 
 static int energy_core(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, float* parts, cudaStream_t st) {
   ctx->jas_valid_for = nullptr;
+  ctx->act_valid_for = nullptr;
+  ctx->act_stored = false;
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_energy(ctx, r, W, e_l, parts, st);
   if (ctx->sys.use_bf) {
     // tensor-core route: G_i first, then a 5-channel orbital pass carrying the G-weighted Laplacian (nqmc_backflow.cu)
@@ -614,6 +620,13 @@ int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normal
   rc = mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, nullptr, n_acc, S(st));
   if (rc) return rc;
   ctx->jas_valid_for = nullptr;
+  ctx->act_valid_for = nullptr;
+  ctx->act_stored = false;
+  // phase B of this step runs at the same positions with the same theta: let the 5-channel pass park the activations the
+  // width-128 reverse pass needs (NQMC_ACT_REUSE=0 keeps the reverse pass's own value sweep)
+  static const bool act_reuse = [] { const char* e = getenv("NQMC_ACT_REUSE"); return !e || atoi(e) != 0; }();
+  struct Want { nqmc_ctx* c; ~Want() { c->want_act = false; } } want{ctx};
+  ctx->want_act = act_reuse;
   if (ctx->sys.kind == NQMC_KIND_ANTISYMMETRIC && !ctx->sys.use_cusp && !ctx->sys.use_bf &&
       (W + 127) / 128 <= ctx->n_blk_walk) {
     // fused: orbital pass, then E_L assembly + header + Jastrow-scalar sums in one kernel
@@ -622,11 +635,14 @@ int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normal
     rc = nq_launch_assemble_stats(ctx, r, W, e_l, ctx->wgt, hdr, S(st));
     if (rc) return rc;
     ctx->jas_valid_for = e_l;
-    return NQMC_OK;
+  } else {
+    rc = energy_core(ctx, r, W, e_l, nullptr, S(st));
+    if (rc) return rc;
+    rc = nq_launch_stats(ctx, e_l, ctx->wgt, W, hdr, S(st));
+    if (rc) return rc;
   }
-  rc = energy_core(ctx, r, W, e_l, nullptr, S(st));
-  if (rc) return rc;
-  return nq_launch_stats(ctx, e_l, ctx->wgt, W, hdr, S(st));
+  if (ctx->act_stored) { ctx->act_valid_for = e_l; ctx->act_W = W; }
+  return NQMC_OK;
 }
 
 int nqmc_walker_step_b(nqmc_ctx* ctx, const float* r, const float* e_l, int64_t W, const double* hdr, double* gsum,

@@ -452,6 +452,7 @@ int nqmc_apply_update(nqmc_ctx* ctx, const double* delta, int64_t P, nqmc_stream
   NQMC_CUDA(cudaSetDevice(ctx->device));
   apply_update_kernel<<<ctx->sm_count, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ctx->theta, delta, (int)P);
   ctx->theta_dirty = true;
+  ctx->act_valid_for = nullptr;
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
 }

@@ -109,6 +109,12 @@ struct nqmc_ctx {
   double* hdr_tmp = nullptr;   // [8]
   double* jas_sums = nullptr;  // [8] sum O, sum E O of the Jastrow scalars (fused walker step)
   const float* jas_valid_for = nullptr;   // e_l pointer the sums belong to (nullptr: not valid)
+  // width-128 reverse pass fed by the energy pass of the same fused step (nqmc_orbital_fwd_pc.cu, BwdOut): want_act asks the
+  // 5-channel kernel to park h1 / h2 / features, act_stored reports that it did, act_valid_for = the e_l pointer they belong to
+  bool want_act = false, act_stored = false;
+  const float* act_valid_for = nullptr;
+  int64_t act_W = 0;
+  float* bw_h2 = nullptr;      // [n_mlp][128][bw_rows] h2 parked by the 5-channel pass
   const float* sigma_dev = nullptr;       // device-resident proposal width (set by nqmc_sample while it runs)
   // NQMC_GUARD=1: guard bands around every scratch buffer (nqmc_debug_check_guards)
   struct Guard { char* base; size_t bytes, padded; const char* name; };

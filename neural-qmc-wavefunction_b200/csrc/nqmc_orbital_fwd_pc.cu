@@ -119,6 +119,13 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) 
 // row-contiguous (so the stores are coalesced and the arrays are K-major GEMM operands for the weight-gradient kernel):
 //   hT[m][unit][row] = h1, dT[m][unit][row] = delta2 = seed W3 (1 - h2^2), fT[m][0..F][row] = [1 | features],
 // and accumulates dW3 += seed h2, db3 += seed in registers (flushed into the CTA's slab at the end).
+// The 5-channel pass (CH = 5, BW false) called with hT != nullptr parks the same per-row activations for a reverse pass
+// that follows at the same positions (fused walker step): hT = h1, dT = h2 (NOT delta2: the seeds need E_L and the inverse
+// matrices, which exist only after this pass -- bwd128_seed_kernel turns h2 into delta2), fT = [1 | features].  The value
+// sweep above is then skipped (H10: 2.67 ms) for a 1.46 ms HBM-bound seed kernel and +0.5 ms here.  The stores sit where they
+// cost least (measured one by one): h1 in the LAST pass's chunk loop, which only reloads layer 1 and waits for the MMAs
+// anyway (+0.12 ms at H10; in pass 0, +0.29), the features after the first pass's chunks while the tensor pipe drains
+// (+0.08; ahead of the first chunk, +0.24), h2 in the epilogue that computes it (+0.28).
 struct BwdOut {
   const float* inv; const float* wgt; const double* hdr; const float* e_l;   // seed = weight * inverse-matrix entry
   float* hT; float* dT; float* fT; float* part;
@@ -406,6 +413,7 @@ __global__ void __launch_bounds__(TCT, 1)
           }
         }
       }
+      const bool st_act = !BW && CH == 5 && bw.hT != nullptr;     // park h1, h2 and the features for the reverse pass
       if constexpr (BW && !C::L1TC) {                            // [1 | x y z | d_a | e_a] of this row, dealt over its four threads
         float* fr = bw.fT + (int64_t)m * 32 * bw.rows_pad + rid;
         const float fv[4] = {1.0f, x, y, z};
@@ -528,6 +536,12 @@ __global__ void __launch_bounds__(TCT, 1)
             float* hr = bw.hT + ((int64_t)m * H + j0) * bw.rows_pad + rid;
             hr[0] = acc[0][0];
             hr[bw.rows_pad] = acc[0][1];
+          } else if constexpr (CH == 5) {
+            if (st_act && pass == NPASS - 1) {                        // last pass: its chunk loop only reloads layer 1, the stores hide behind the MMAs
+              float* hr = bw.hT + ((int64_t)m * H + j0) * bw.rows_pad + rid;
+              __stcs(hr, acc[0][0]);
+              __stcs(hr + bw.rows_pad, acc[0][1]);
+            }
           }
           const uint32_t b = g % NBUF, u = g / NBUF;
           if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
@@ -544,6 +558,24 @@ __global__ void __launch_bounds__(TCT, 1)
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(full0 + 8 * b);
+        }
+        // parked features: stored here, while the tensor pipe drains, not ahead of the tile's first chunk
+        if constexpr (!BW && CH == 5) {
+          if (st_act && pass == 0) {
+            float* fr = bw.fT + (int64_t)m * 32 * bw.rows_pad + rid;
+            const float fv[4] = {1.0f, x, y, z};
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              if (f == quarter) fr[(int64_t)f * bw.rows_pad] = fv[f];
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+              float dd, ex;
+              if constexpr (C::FEAT_SMEM) { const float4 fa = featA[a * ROWS + row]; dd = fa.x; ex = fa.y; }
+              else { dd = fdd[a]; ex = fex[a]; }
+              if (((4 + a) & 3) == quarter) fr[(int64_t)(4 + a) * bw.rows_pad] = dd;
+              if (((4 + NA + a) & 3) == quarter) fr[(int64_t)(4 + NA + a) * bw.rows_pad] = ex;
+            }
+          }
         }
         // ---- epilogue of this pass: output units [NT pass, NT pass + NT) ----------------------------------------
         mbar_wait(dfull, ep & 1);
@@ -574,6 +606,13 @@ __global__ void __launch_bounds__(TCT, 1)
               dst[0] = d2.x;
               dst[bw.rows_pad] = d2.y;
               continue;
+            }
+            if constexpr (!BW && CH == 5) {
+              if (st_act) {
+                float* dst = bw.dT + ((int64_t)m * H + jb + j) * bw.rows_pad + rid;
+                __stcs(dst, h.x);
+                __stcs(dst + bw.rows_pad, h.y);
+              }
             }
             out2[0] = nq_fma2(w3, h, out2[0]);
             if constexpr (CH >= 4) {
@@ -677,14 +716,14 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* 
 }
 
 template <int H, int CH, bool GW>
-int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st) {
+int dispatch_na(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* G, cudaStream_t st, const BwdOut bw = BwdOut{}) {
   switch (ctx->sys.A) {                // the number of nuclei is a template parameter: the feature loop is unrolled
-    case 1: return launch_t<H, 1, CH, GW>(ctx, r, W, phi, G, st);
-    case 2: return launch_t<H, 2, CH, GW>(ctx, r, W, phi, G, st);
-    case 4: return launch_t<H, 4, CH, GW>(ctx, r, W, phi, G, st);
-    case 6: return launch_t<H, 6, CH, GW>(ctx, r, W, phi, G, st);
-    case 8: return launch_t<H, 8, CH, GW>(ctx, r, W, phi, G, st);
-    case 10: return launch_t<H, 10, CH, GW>(ctx, r, W, phi, G, st);
+    case 1: return launch_t<H, 1, CH, GW>(ctx, r, W, phi, G, st, bw);
+    case 2: return launch_t<H, 2, CH, GW>(ctx, r, W, phi, G, st, bw);
+    case 4: return launch_t<H, 4, CH, GW>(ctx, r, W, phi, G, st, bw);
+    case 6: return launch_t<H, 6, CH, GW>(ctx, r, W, phi, G, st, bw);
+    case 8: return launch_t<H, 8, CH, GW>(ctx, r, W, phi, G, st, bw);
+    case 10: return launch_t<H, 10, CH, GW>(ctx, r, W, phi, G, st, bw);
     default: return NQMC_ERR_UNSUPPORTED;
   }
 }
@@ -710,16 +749,23 @@ int nq_launch_orb_fwd_bw128(nqmc_ctx* ctx, const float* r, const float* wgt, con
 // Value (channels == 1) or 5-channel pass.  Without G: hidden width 128 only (width 64 has its own kernels).  With G
 // (backflow, G-weighted Laplacian channel): width 64 or 128.  Returns NQMC_ERR_UNSUPPORTED otherwise (the caller falls
 // back to the FP32 FFMA kernels).
+// ctx->want_act (set by the fused walker step around its energy pass; 5-channel pass, width 128, reverse-pass scratch
+// reserved): also park h1 / h2 / features (see BwdOut) and report it in ctx->act_stored.
 int nq_launch_orb_fwd_pc(nqmc_ctx* ctx, const float* r, int64_t W, int channels, float* phi, const float* G, cudaStream_t st) {
   const int H = ctx->sys.H;
+  BwdOut bw{};
+  const bool park = ctx->want_act && channels == 5 && H == 128 && ctx->bw_h != nullptr && ctx->bw_h2 != nullptr &&
+                    nq_bwd128_rows(ctx, W) <= ctx->bw_rows;
+  if (park) { bw.hT = ctx->bw_h; bw.dT = ctx->bw_h2; bw.fT = ctx->bw_f; bw.rows_pad = ctx->bw_rows; bw.part = ctx->part_mlp; }
+  int rc = NQMC_ERR_UNSUPPORTED;
   if (G != nullptr) {
     if (channels != 5 || 3 + 2 * ctx->sys.A > H) return NQMC_ERR_UNSUPPORTED;
     if (H == 64 && ctx->sys.A <= 6) return dispatch_na<64, 5, true>(ctx, r, W, phi, G, st);
-    if (H == 128) return dispatch_na<128, 5, true>(ctx, r, W, phi, G, st);
-    return NQMC_ERR_UNSUPPORTED;
+    if (H == 128) rc = dispatch_na<128, 5, true>(ctx, r, W, phi, G, st, bw);
+  } else if (H == 128) {
+    if (channels == 1) return dispatch_na<128, 1, false>(ctx, r, W, phi, nullptr, st);
+    if (channels == 5) rc = dispatch_na<128, 5, false>(ctx, r, W, phi, nullptr, st, bw);
   }
-  if (H != 128) return NQMC_ERR_UNSUPPORTED;
-  if (channels == 1) return dispatch_na<128, 1, false>(ctx, r, W, phi, nullptr, st);
-  if (channels == 5) return dispatch_na<128, 5, false>(ctx, r, W, phi, nullptr, st);
-  return NQMC_ERR_UNSUPPORTED;
+  if (rc == NQMC_OK && park) ctx->act_stored = true;
+  return rc;
 }

@@ -942,6 +942,7 @@ int nq_adam_step(nqmc_ctx* ctx, const double* gsum, const double* hdr, float* m,
   NQMC_LAUNCH_CHECK();
   const float bc1 = 1.0f - powf(0.9f, (float)count), bc2 = 1.0f - powf(0.999f, (float)count);
   ctx->theta_dirty = true;                       // see nq_launch_pdl_guarded
+  ctx->act_valid_for = nullptr;
   adam_apply_kernel<<<(P + 255) / 256, 256, 0, st>>>(gsum, hdr, ctx->part_walk, nblk, P, ctx->theta, m, v, lr, clip, bc1, bc2,
                                                      norm_out);
   NQMC_LAUNCH_CHECK();

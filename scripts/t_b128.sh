@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "128" 2>&1 | tail -25
-timeout 300 python scripts/exp/profile_configs.py 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py tests/test_gpu_guard.py tests/test_gpu_vmc.py -x -q 2>&1 | tail -15
+timeout 300 python scripts/exp/profile_configs.py 2>&1 | tail -8
+NQMC_ACT_REUSE=0 timeout 300 python scripts/exp/profile_configs.py 2>&1 | tail -5

@@ -147,3 +147,32 @@ def test_h4_dissociation_sweep_16_geometries():
     # energies differ between geometries (they are not accidentally sharing a context)
     en = np.array([o["energy"] for o in res])
     assert len(np.unique(np.round(en, 6))) == 16
+
+
+@pytest.mark.parametrize("case", [dict(n_atoms=4, hidden=128), dict(n_atoms=6, hidden=128, use_cusp=True, use_backflow=True)],
+                         ids=["H4-h128", "H6-h128-bf-cusp"])
+def test_reverse_pass_from_parked_activations_equals_value_sweep(case):
+    """Width 128: the fused step's reverse pass reads h1 / h2 / features parked by the 5-channel energy pass
+    (bwd128_seed_kernel); an energy call between the two phases invalidates them and the reverse pass runs its own value
+    sweep.  Both must give the same gradient sums (tensor-core kernels on both sides: 3xTF32 vs FP32 layer 1)."""
+    from _util import make_case, make_context
+    W = 1000
+    s, net, theta, r = make_case(W=W, burn=5, **case)
+    ctx = make_context(s, net)
+    ctx.set_params(theta)
+    out = []
+    for invalidate in (False, True):
+        soa = ctx.to_soa(r)
+        _, la = ctx.log_psi(soa)
+        logp = ctx.upload((2 * la.numpy()).astype(np.float32))
+        e, hdr, g = ctx.empty(W), ctx.empty(8, np.float64), ctx.empty(ctx.P, np.float64)
+        ctx.walker_step_a(soa, logp, 0.3, e, hdr, seed=11, step=0)
+        if invalidate:
+            ctx.local_energy(soa)                                      # any energy pass drops the parked activations
+        ctx.walker_step_b(soa, e, hdr, g)
+        out.append((e.numpy(ctx.stream).copy(), g.numpy(ctx.stream).copy()))
+    assert np.array_equal(out[0][0], out[1][0])
+    ga, gb = out
+    scale = max(1.0, float(np.max(np.abs(gb[1]))))
+    assert np.max(np.abs(ga[1] - gb[1])) <= 2e-5 * scale, (np.max(np.abs(ga[1] - gb[1])), scale)
+    assert np.any(ga[1] != gb[1])                                       # the two routes really are different kernels
