@@ -102,13 +102,15 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {   // MN-m
 }
 // D=f32, A=B=tf32, both K-major, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-// G2: A and B MN-major, M = 64 (the 64 h1 units; half the A-operand traffic of M = 128, same UMMA time).
-// An M = 64 accumulator row u lives in TMEM lane (u / 16) * 32 + u % 16 (probed: scripts/exp/m64_probe.cu).
-// the same with N = 128: B' = [delta2_hi | delta2_lo] (the lo buffer follows the hi buffer: two more 32-unit atom columns), so
-// one UMMA yields a_hi b_hi in columns 0-63 and a_hi b_lo in columns 64-127 -- two UMMAs per k-step instead of three, and
-// the A operand is read from shared memory twice instead of three times (the kernel is shared-memory-bandwidth-bound)
-constexpr uint32_t IDESC_MN128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-constexpr uint32_t IDESC_MN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+// G2 = h1^T delta2: A and B MN-major, K = rows.  Round 2a ran it as M = 64 (the 64 h1 units; an M = 64 accumulator row u lives
+// in TMEM lane (u / 16) * 32 + u % 16, probed: scripts/exp/m64_probe.cu -- G1^T still does) with B' = [delta2_hi | delta2_lo]
+// as N = 128 (the lo buffer follows the hi buffer: two more 32-unit atom columns): a_hi b_hi in columns 0-63, a_hi b_lo in
+// columns 64-127, plus a second UMMA a_lo b_hi.  Round 2b: the same concatenation on the A side, A' = [h1_hi ; h1_lo] as
+// M = 128 (hM_lo follows hM_hi): ONE UMMA per k-step yields a_hi b_hi | a_hi b_lo in lanes 0-63 and a_lo b_hi | a_lo b_lo in
+// lanes 64-127 (accumulator row = lane for M = 128).  An M = 64 UMMA occupies the tensor pipe as long as an M = 128 one, so
+// G2 drops from 16 x (N128 + N64) to 16 x N128, and delta2_hi is read from shared memory once instead of twice: reverse
+// kernel 153.5 -> 148.2 us.
+constexpr uint32_t IDESC_MN128M = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -472,14 +474,13 @@ __global__ void __launch_bounds__(TCT, 1)
       }
       tile_barrier();                                    // P3 done: h1 in hM, delta2 in dM, features in fT
       if (iw == 2) {
-        const uint64_t ah = umma_desc_mn(sbase + mp.hM_hi), al = umma_desc_mn(sbase + mp.hM_lo);
-        const uint64_t bh = umma_desc_mn(sbase + mp.dM_hi);   // N = 128 reads on into dM_lo (contiguous: see SmemMap)
+        const uint64_t ah = umma_desc_mn(sbase + mp.hM_hi);   // M = 128 reads on into hM_lo, N = 128 into dM_lo (contiguous: SmemMap)
+        const uint64_t bh = umma_desc_mn(sbase + mp.dM_hi);
 #pragma unroll 1
         for (int ks = 0; ks < ROWS / 8; ++ks) {          // G2 += h1^T delta2   (both operands MN-major, K = 8 rows per UMMA)
           const uint64_t ko = (uint64_t)((ks * 2 * MN_SBO) >> 4);
           const uint32_t acc = (n_done == 0 && ks == 0) ? 0u : 1u;
-          umma_ss(tmem_base + C_G2, ah + ko, bh + ko, IDESC_MN128, acc, leader);   // a_hi [b_hi | b_lo]
-          umma_ss(tmem_base + C_G2, al + ko, bh + ko, IDESC_MN, 1u, leader);       // a_lo b_hi -> columns 0-63
+          umma_ss(tmem_base + C_G2, ah + ko, bh + ko, IDESC_MN128M, acc, leader);  // [a_hi ; a_lo] [b_hi | b_lo]
         }
         umma_commit(bar_g2, leader);
       }
@@ -707,13 +708,23 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll
       for (int j = 0; j < UPT; ++j) v2[j] = 0.f;          // this CTA had no tile: the slab must still be defined
     }
-    // M = 64 accumulators: lanes 0-15, 32-47, 64-79, 96-111 hold units 0-15, 16-31, 32-47, 48-63
+    // G2 (M = 128): lane r < 64 holds the h1_hi products of unit r, lane 64 + r the h1_lo products: the upper half hands its
+    // sums to the lower half through the (now idle) hM buffer
+    {
+      float* xch = reinterpret_cast<float*>(hM_hi);      // [64][H]
+      if (row >= H) {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) xch[(row - H) * H + c0 + j] = v2[j];
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(TCW) : "memory");      // workers only
+      if (row < H) {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) slab[o_W2 + row * H + c0 + j] = v2[j] + xch[row * H + c0 + j];
+      }
+    }
+    // G1^T, M = 64 accumulators: lanes 0-15, 32-47, 64-79, 96-111 hold units 0-15, 16-31, 32-47, 48-63
     const bool lane_ok = (row & 16) == 0;
     const int unit = (row >> 5) * 16 + (row & 15);
-    if (lane_ok) {
-#pragma unroll
-      for (int j = 0; j < UPT; ++j) slab[o_W2 + unit * H + c0 + j] = v2[j];
-    }
     // G1^T: lane = delta1 unit, column = feature (column F: ones -> db1); 8 columns per read,
     // column groups dealt over the quarters
     for (int cg = quarter; cg < mp.n_g1 / 8; cg += NQ) {
