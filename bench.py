@@ -252,6 +252,17 @@ def sr_iteration_rate_h4(iters=3):
             "last_metrics": m, "timing": "host wall clock around VMCOptimizer.step"}
 
 
+def other_configs_sharded(flush, rank, world):
+    """configs[2] and configs[4] -- the two BASELINE configs quoted on 8 GPUs -- weak-scaled over `world` ranks at their
+    per-GPU sizes (262,144 / 8 and 1,048,576 / 8 walkers per GPU).  Collective: every rank calls this; device time, max
+    over ranks.  The peak fractions are added by rank 0 (add_fracs)."""
+    out = {}
+    for name, args_ in (("configs[2] H6 +backflow +cusp, orbital MLP 15-128-128-1 x6", (6, 128, 32768, True, True)),
+                        ("configs[4] H10, orbital MLP 23-128-128-1 x10", (10, 128, 131072, False, False))):
+        out[name] = time_fused_step(*args_, steps=5, warm=2, flush=flush, rank=rank, world=world)
+    return out
+
+
 def other_configs(flush, peak3, ffma_peak):
     """The BASELINE configs that are not the headline, on ONE GPU at their per-GPU sizes (configs[2] and [4] name 8
     GPUs: 262,144 / 8 and 1,048,576 / 8 walkers), same event timing and L2 flush as the headline."""
@@ -469,6 +480,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
+    sharded = None
+    if world > 1 and peer and not args.no_extras:                # configs[2] / configs[4] over the same ranks
+        try:
+            sharded = other_configs_sharded(flush, rank, world)
+        except Exception as e:      # report, do not hide
+            sharded = {"error": repr(e)}
+
     out = None
     if rank == 0:
         flops_step, flops_value = algorithmic_flops_per_walker_step(N_ATOMS, HIDDEN, mol.n_electrons)
@@ -561,6 +579,12 @@ def run_ours(args):
                 out["sr_iteration_h4"] = sr_iteration_rate_h4()
             except Exception as e:
                 out["sr_iteration_h4"] = {"error": repr(e)}
+        if sharded is not None:
+            for d in sharded.values():
+                if isinstance(d, dict) and "achieved_tflops" in d:
+                    d["frac_of_tf32_over_3"] = d["achieved_tflops"] / peak3
+                    d["note"] = "per-GPU figures (achieved_tflops, value_per_gpu) and the whole-job value over n_gpus ranks"
+            out["other_configs"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_walkers, steps=2, warmup=1)
     if world > 1:
@@ -622,10 +646,13 @@ def measure_tf32_peak(dev, local=0, sizes=(4096, 8192), reps=50):
     return rec
 
 
-def time_fused_step(n_atoms, hidden, W, cusp, bf, steps, warm, flush, sigma=0.3):
+def time_fused_step(n_atoms, hidden, W, cusp, bf, steps, warm, flush, sigma=0.3, rank=0, world=1):
     """Device time of nqmc_walker_step for one BASELINE config at its per-GPU size (events on the launching stream,
-    L2 flushed between timed steps).  -> dict"""
+    L2 flushed between timed steps).  world > 1: every rank runs its own W walkers (global ids rank*W ...), hdr and gsum
+    are summed over ranks inside the step by the peer-memory all-reduce, the time is the max over ranks.  -> dict"""
     import torch
+    import torch.distributed as dist
+    from nqmc_b200 import parallel
     from nqmc_b200.systems import hydrogen_chain
     from nqmc_b200.wavefunction import AntisymmetricWavefunction
     from nqmc_b200 import random as nqrandom
@@ -635,29 +662,43 @@ def time_fused_step(n_atoms, hidden, W, cusp, bf, steps, warm, flush, sigma=0.3)
     theta = ravel(wf.init(nqrandom.PRNGKey(SEED)))
     ctx = wf.context(mol)
     ctx.set_params(theta)
-    r = ctx.to_soa(initial_walkers(mol, W, 0))
+    lo = rank * W
+    if world > 1 and not parallel.attach_peer_memory(ctx):
+        raise RuntimeError("peer-memory communicator could not be attached")
+    r = ctx.to_soa(initial_walkers(mol, W, lo))
     _, la = ctx.log_psi(r)
     logp = ctx.upload((2.0 * la.numpy()).astype(np.float32))
     e_l, hdr, gsum = ctx.empty(W), ctx.empty(8, np.float64), ctx.empty(ctx.P, np.float64)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
     for t in range(30):
-        ctx.mh_step(r, logp, sigma, seed=SEED, step=t)
+        ctx.mh_step(r, logp, sigma, seed=SEED, step=t, walker_id0=lo)
     for t in range(warm):
-        ctx.walker_step(r, logp, sigma, e_l, hdr, gsum, seed=SEED, step=100 + t)
-    torch.cuda.synchronize()
+        ctx.walker_step(r, logp, sigma, e_l, hdr, gsum, seed=SEED, step=100 + t, walker_id0=lo)
+    sync()
     l0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for t, (a, b) in enumerate(ev):
         flush.fill_(1.0)
         a.record()
-        ctx.walker_step(r, logp, sigma, e_l, hdr, gsum, seed=SEED, step=1000 + t)
+        ctx.walker_step(r, logp, sigma, e_l, hdr, gsum, seed=SEED, step=1000 + t, walker_id0=lo)
         b.record()
-    torch.cuda.synchronize()
+    sync()
     ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
     fl, _ = algorithmic_flops_per_walker_step(n_atoms, hidden, n_atoms, backflow=bf)
     h = hdr.numpy()
     out = {"walkers_per_gpu": W, "P": ctx.P, "ms_per_step": ms, "value_per_gpu": W / (ms * 1e-3), "unit": "walker-steps/s",
+           "n_gpus": world, "global_walkers": world * W, "value": world * W / (ms * 1e-3),
            "algorithmic_flop_per_walker_step": fl, "achieved_tflops": fl * W / (ms * 1e-3) / 1e12,
            "launches_per_step": (ctx.launch_count() - l0) / steps, "mean_E_L": h[1] / max(h[0], 1), "n_bad": h[4]}
+    sync()                                                     # no rank frees its inbox while a peer may still push
     del ctx
     return out
 

@@ -209,21 +209,36 @@ __global__ void __launch_bounds__(TCT, 1)
       ny = r[(int64_t)(3 * e + 1) * W + w];
       nz = r[(int64_t)(3 * e + 2) * W + w];
     };
-    if (chunk < n_items) fetch(chunk);
-    for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
-      const int i = (int)(item % ns);
-      const int64_t w0 = (item / ns) * ROWS;
-      const float x = nx, y = ny, z = nz;
-      if (item + n_chunks < n_items) fetch(item + n_chunks);
-      // per nucleus: d, exp(-d), unit vector, 2/d -- in registers for all 8 chunks.  With s = wd - e we the five
-      // channels of (d, e) contribute  value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we   (7 FMA, not 10).
-      float fdd[NA], fex[NA], fux[NA], fuy[NA], fuz[NA], fti[NA];
+    // per nucleus: d, exp(-d), unit vector, 2/d -- in registers for all 8 chunks.  With s = wd - e we the five
+    // channels of (d, e) contribute  value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we   (7 FMA, not 10).
+    float x = 0.f, y = 0.f, z = 0.f;
+    float fdd[NA], fex[NA], fux[NA], fuy[NA], fuz[NA], fti[NA];
+    auto features = [&]() {                                    // of the tile whose positions sit in (nx, ny, nz)
+      x = nx; y = ny; z = nz;
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const float dx = x - s.R[3 * a], dy = y - s.R[3 * a + 1], dz = z - s.R[3 * a + 2];
         const float dd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
         const float inv = 1.0f / dd;
         fdd[a] = dd; fex[a] = __expf(-dd); fux[a] = dx * inv; fuy[a] = dy * inv; fuz[a] = dz * inv; fti[a] = 2.0f * inv;
+      }
+    };
+    // AHEAD: the features of tile t+1 are formed while the last UMMAs of tile t are in flight (they stay live across the
+    // epilogue: 6 registers per nucleus, which the 112-register budget has room for up to 4 nuclei)
+    constexpr bool AHEAD = NA <= 4;
+    if (chunk < n_items) {
+      fetch(chunk);
+      if (AHEAD) {
+        features();
+        if (chunk + n_chunks < n_items) fetch(chunk + n_chunks);
+      }
+    }
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
+      const int i = (int)(item % ns);
+      const int64_t w0 = (item / ns) * ROWS;
+      if (!AHEAD) {
+        features();
+        if (item + n_chunks < n_items) fetch(item + n_chunks);
       }
 #pragma unroll 2
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
@@ -277,6 +292,12 @@ __global__ void __launch_bounds__(TCT, 1)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * b);
+      }
+      // the last chunks' UMMAs are still in flight: the features of the next tile (the chunk loop is done with this
+      // tile's) fill the wait, and the positions of the tile after that are requested
+      if (AHEAD && item + n_chunks < n_items) {
+        features();
+        if (item + 2 * (int64_t)n_chunks < n_items) fetch(item + 2 * (int64_t)n_chunks);
       }
       // ---- epilogue ------------------------------------------------------------------------------------------
       mbar_wait(dfull, t & 1);
