@@ -448,10 +448,20 @@ def run_ours(args):
     h2d = Wl * nn * 4 + Wl * 4
     d2h = Wl * nn * 4 + Wl * 4 + Wl * 4 + 8 * 8 + ctx.P * 8
 
-    def e2e_step(s):
-        if world == 1 or peer:                                 # the C-ABI host entry point itself
-            ctx.walker_step_host(r_host.numpy(), logp_host.numpy(), SIGMA, e_host.numpy(), hdr_host.numpy(),
-                                 g_host.numpy(), seed=SEED, step=s, walker_id0=lo)
+    rh, lh, eh, hh, gh = (x.numpy() for x in (r_host, logp_host, e_host, hdr_host, g_host))
+    pipelined = [os.environ.get("NQMC_E2E_SYNC", "0") != "1"]
+
+    def e2e_step(s, last=False):
+        if (world == 1 or peer) and pipelined[0]:              # the C-ABI host entry points, pipelined form: every step's
+            # inputs go H2D and its results D2H inside the loop; the upload of step s+1's walkers (available once phase A
+            # of step s has come home) overlaps the reverse pass of step s
+            ctx.walker_step_host_async(rh, lh, SIGMA, eh, hh, gh, seed=SEED, step=s, walker_id0=lo)
+            ctx.walker_step_host_wait(ctx.WAIT_PHASE_A)
+            if not last:
+                ctx.walker_step_host_upload(rh, lh)
+            ctx.walker_step_host_wait(ctx.WAIT_ALL)
+        elif world == 1 or peer:                               # synchronous host entry point
+            ctx.walker_step_host(rh, lh, SIGMA, eh, hh, gh, seed=SEED, step=s, walker_id0=lo)
         else:                                                  # same copies, phases split around the all-reduces
             ra = r_host.to(dev, non_blocking=True)
             lp = logp_host.to(dev, non_blocking=True)
@@ -467,18 +477,25 @@ def run_ours(args):
             g_host.copy_(gsum, non_blocking=True)
             torch.cuda.synchronize()
 
-    for i in range(3):
-        e2e_step((1 << 21) + i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step((1 << 22) + i)
-    e2e_s = time.perf_counter() - t0                           # this rank's own finish (every step ends synchronised);
-    barrier()                                                  # the max over ranks is taken below
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    def e2e_run(base):
+        for i in range(3):
+            e2e_step(base + i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(base + 64 + i, last=(i == args.steps - 1))
+        dt = time.perf_counter() - t0                          # this rank's own finish (every step ends synchronised);
+        barrier()                                              # the max over ranks is taken below
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    e2e_s = e2e_run(1 << 21)
+    e2e_sync_s = None
+    if pipelined[0] and (world == 1 or peer):                  # the synchronous entry point, for comparison
+        pipelined[0] = False
+        e2e_sync_s = e2e_run(1 << 22)
+        pipelined[0] = True
 
     sharded = None
     if world > 1 and peer and not args.no_extras:                # configs[2] / configs[4] over the same ranks
@@ -522,8 +539,13 @@ def run_ours(args):
                                     "vmc.py:247); only sampled steps counted; L2 not flushed"},
             "clocks": clocks,
             "e2e": {"value": world * Wl * args.steps / e2e_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "path": "nqmc_walker_step_host (C ABI, pinned host buffers)" if (world == 1 or peer)
-                    else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host"},
+                    "d2h_bytes_per_step": d2h,
+                    "path": ("nqmc_walker_step_host_async / _wait / _upload (C ABI, pinned host buffers; the H2D of step s+1's "
+                             "walkers overlaps the reverse pass of step s)" if e2e_sync_s is not None else
+                             "nqmc_walker_step_host (C ABI, pinned host buffers)") if (world == 1 or peer)
+                    else "pinned host buffers -> nqmc_walker_step_a/b + NCCL all-reduce -> host",
+                    "synchronous_value": (world * Wl * args.steps / e2e_sync_s) if e2e_sync_s else None,
+                    "synchronous_path": "nqmc_walker_step_host (one blocking call per step)" if e2e_sync_s else None},
             "gpu_launches": launches,
             "roofline": ({"bound": "tensor", "kernel": "orb_lap_pc_kernel<4> (orbital forward value+grad+Laplacian; H x H layer = tcgen05 3xTF32 with A in TMEM, input layer = FFMA)",
                           "achieved": ach, "peak": peak3, "unit": "TFLOP/s", "frac": (ach / peak3) if ach else None,

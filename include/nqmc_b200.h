@@ -210,6 +210,27 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, co
                           const float* uniforms_host, uint64_t seed, uint64_t step, int64_t walker_id0, float sigma,
                           int64_t W, float* e_l_host, double* hdr_host, double* gsum_host, nqmc_stream stream);
 
+/* Pipelined form of the host-buffer step, for a host loop that owns the walkers (the reference's VMCOptimizer.step /
+ * MetropolisSampler.sample callers, src/nqmc/optimizer/vmc.py:238-253): the walkers, log|psi|^2, E_L and the header are
+ * final after phase A and travel home while the reverse pass (phase B) still runs, and the next step's walkers -- which
+ * do not depend on the gradient -- can travel to the device during that reverse pass.
+ *   nqmc_walker_step_host_async : nqmc_walker_step_host without the final synchronisation.
+ *   nqmc_walker_step_host_wait  : block until the phase-A outputs (r, logp, e_l, hdr: NQMC_WAIT_PHASE_A) or everything
+ *                                 (gsum too: NQMC_WAIT_ALL) of the last _async call is in the host buffers.
+ *   nqmc_walker_step_host_upload: start the H2D copy + AoS->SoA conversion of the NEXT step's inputs on the context's
+ *                                 own copy stream.  Call it after nqmc_walker_step_host_wait(ctx, NQMC_WAIT_PHASE_A);
+ *                                 the next _async / _host call that names the same host pointers and W finds its
+ *                                 inputs staged and skips its own copy (any other call copies as usual).
+ * The host buffers must stay valid (pinned for real overlap) until the matching wait returns. */
+#define NQMC_WAIT_PHASE_A 0
+#define NQMC_WAIT_ALL 1
+int nqmc_walker_step_host_async(nqmc_ctx* ctx, float* r_aos_host, float* logp_host, const float* normals_aos_host,
+                                const float* uniforms_host, uint64_t seed, uint64_t step, int64_t walker_id0, float sigma,
+                                int64_t W, float* e_l_host, double* hdr_host, double* gsum_host, nqmc_stream stream);
+int nqmc_walker_step_host_wait(nqmc_ctx* ctx, int what);
+int nqmc_walker_step_host_upload(nqmc_ctx* ctx, const float* r_aos_host, const float* logp_host,
+                                 const float* normals_aos_host, const float* uniforms_host, int64_t W);
+
 /* ---- Stochastic Reconfiguration ----------------------------------------------------------
  * C[M][N] = alpha * A B^T + diag * I at fp32-grade accuracy on the tensor cores (tcgen05 kind::tf32, three products
  * per fp32 product, fp32 accumulation in TMEM), operands streamed by TMA.  A is [M][lda], B is [N][ldb], both with the

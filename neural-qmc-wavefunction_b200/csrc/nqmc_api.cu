@@ -112,13 +112,14 @@ void scratch_free(nqmc_ctx* c, void* p) {
 }
 
 void free_scratch(nqmc_ctx* c) {
-  void* ptrs[] = {c->bfw, c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->nrm_soa,
+  void* ptrs[] = {c->bfw, c->gbf, c->x_cur, c->x_prop, c->vvec, c->r_prop, c->phi, c->inv, c->logabs, c->sign, c->e_scratch, c->wgt, c->r_soa, c->r_soa2, c->nrm_soa,
                   c->aos_stage, c->uni_stage, c->logp_stage, c->nacc_stage, c->hdr_stage, c->gsum_stage, c->part_walk,
                   c->part_mlp, c->hdr_tmp, c->jas_sums, c->bw_h, c->bw_d, c->bw_e, c->bw_f, c->bw_h2, c->l1cache};
   for (void* p : ptrs) scratch_free(c, p);
   c->guards.clear();
   c->x_cur = c->x_prop = c->vvec = c->gbf = c->bfw = nullptr;
-  c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->nrm_soa = nullptr;
+  c->r_prop = c->phi = c->inv = c->logabs = c->sign = c->e_scratch = c->wgt = c->r_soa = c->r_soa2 = c->nrm_soa = nullptr;
+  c->up_pending = false;
   c->aos_stage = c->uni_stage = c->logp_stage = c->nacc_stage = nullptr;
   c->hdr_stage = c->gsum_stage = c->part_walk = c->hdr_tmp = c->jas_sums = nullptr;
   c->jas_valid_for = nullptr;
@@ -269,6 +270,9 @@ int nqmc_destroy(nqmc_ctx* ctx) {
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
+  if (ctx->ev_all_done) cudaEventDestroy(ctx->ev_all_done);
   for (int k = 0; k < nqmc_ctx::PROF_KINDS; ++k)
     for (int i = 0; i < nqmc_ctx::PROF_RING; ++i)
       for (int e = 0; e < 2; ++e)
@@ -301,6 +305,7 @@ int nqmc_reserve(nqmc_ctx* ctx, int64_t W) {
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->e_scratch), w * f, "e_scratch"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->wgt), w * f, "wgt"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->r_soa), nn * w * f, "r_soa"));
+  NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->r_soa2), nn * w * f, "r_soa2"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->nrm_soa), nn * w * f, "nrm_soa"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->aos_stage), nn * w * f, "aos_stage"));
   NQMC_CUDA(scratch_alloc(ctx, reinterpret_cast<void**>(&ctx->uni_stage), w * f, "uni_stage"));
@@ -687,31 +692,75 @@ int nqmc_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, nqmc_stream st)
   return nq_comm_allreduce(ctx, vec, len, S(st));
 }
 
-int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float* normals_aos, const float* uniforms,
-                          uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, double* hdr,
-                          double* gsum, nqmc_stream st_) {
-  int rc = check_w(ctx, W);
-  if (rc) return rc;
-  if (!r_aos || !logp || !e_l || !hdr || !gsum) return NQMC_ERR_ARG;
-  NQMC_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = S(st_);
+namespace {
+int host_streams(nqmc_ctx* ctx) {
+  if (ctx->side_stream) return NQMC_OK;
+  NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+  NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_phase_a, cudaEventDisableTiming));
+  NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
+  NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
+  NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_all_done, cudaEventDisableTiming));
+  return NQMC_OK;
+}
+
+// host inputs of one step -> device staging (AoS -> SoA for the walkers and the normals), on stream st
+int stage_inputs(nqmc_ctx* ctx, const float* r_aos, const float* logp, const float* normals_aos, const float* uniforms,
+                 int64_t W, float* r_soa, cudaStream_t st) {
   const size_t nn = 3 * (size_t)ctx->sys.N, w = (size_t)W, f = sizeof(float);
   NQMC_CUDA(cudaMemcpyAsync(ctx->aos_stage, r_aos, nn * w * f, cudaMemcpyHostToDevice, st));
-  rc = nq_aos_soa(ctx, ctx->aos_stage, ctx->r_soa, W, true, st);
+  int rc = nq_aos_soa(ctx, ctx->aos_stage, r_soa, W, true, st);
   if (rc) return rc;
-  const float* nrm = nullptr;
   if (normals_aos) {
     NQMC_CUDA(cudaMemcpyAsync(ctx->aos_stage, normals_aos, nn * w * f, cudaMemcpyHostToDevice, st));
     rc = nq_aos_soa(ctx, ctx->aos_stage, ctx->nrm_soa, W, true, st);
     if (rc) return rc;
-    nrm = ctx->nrm_soa;
   }
-  const float* uni = nullptr;
-  if (uniforms) {
-    NQMC_CUDA(cudaMemcpyAsync(ctx->uni_stage, uniforms, w * f, cudaMemcpyHostToDevice, st));
-    uni = ctx->uni_stage;
-  }
+  if (uniforms) NQMC_CUDA(cudaMemcpyAsync(ctx->uni_stage, uniforms, w * f, cudaMemcpyHostToDevice, st));
   NQMC_CUDA(cudaMemcpyAsync(ctx->logp_stage, logp, w * f, cudaMemcpyHostToDevice, st));
+  return NQMC_OK;
+}
+}  // namespace
+
+int nqmc_walker_step_host_upload(nqmc_ctx* ctx, const float* r_aos, const float* logp, const float* normals_aos,
+                                 const float* uniforms, int64_t W) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r_aos || !logp) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if ((rc = host_streams(ctx))) return rc;
+  cudaStream_t up = ctx->up_stream;
+  // aos_stage / logp_stage / nrm_soa / uni_stage are free once the phase-A results of the step in flight have gone home
+  // (ev_side_done); its reverse pass keeps reading r_soa, which is why the walkers go into the second buffer
+  if (ctx->host_step_issued) NQMC_CUDA(cudaStreamWaitEvent(up, ctx->ev_side_done, 0));
+  rc = stage_inputs(ctx, r_aos, logp, normals_aos, uniforms, W, ctx->r_soa2, up);
+  if (rc) return rc;
+  NQMC_CUDA(cudaEventRecord(ctx->ev_upload, up));
+  ctx->up_pending = true;
+  ctx->up_r = r_aos; ctx->up_logp = logp; ctx->up_nrm = normals_aos; ctx->up_uni = uniforms; ctx->up_W = W;
+  return NQMC_OK;
+}
+
+int nqmc_walker_step_host_async(nqmc_ctx* ctx, float* r_aos, float* logp, const float* normals_aos, const float* uniforms,
+                                uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, double* hdr,
+                                double* gsum, nqmc_stream st_) {
+  int rc = check_w(ctx, W);
+  if (rc) return rc;
+  if (!r_aos || !logp || !e_l || !hdr || !gsum) return NQMC_ERR_ARG;
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  if ((rc = host_streams(ctx))) return rc;
+  cudaStream_t st = S(st_);
+  const size_t nn = 3 * (size_t)ctx->sys.N, w = (size_t)W, f = sizeof(float);
+  bool staged = false;
+  if (ctx->up_pending) {
+    NQMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_upload, 0));     // also orders an unmatched upload's use of the staging buffers
+    staged = ctx->up_r == r_aos && ctx->up_logp == logp && ctx->up_nrm == normals_aos && ctx->up_uni == uniforms && ctx->up_W == W;
+    ctx->up_pending = false;
+    if (staged) std::swap(ctx->r_soa, ctx->r_soa2);
+  }
+  if (!staged && (rc = stage_inputs(ctx, r_aos, logp, normals_aos, uniforms, W, ctx->r_soa, st))) return rc;
+  const float* nrm = normals_aos ? ctx->nrm_soa : nullptr;
+  const float* uni = uniforms ? ctx->uni_stage : nullptr;
   rc = nqmc_walker_step_a(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
                           ctx->hdr_stage, st_);
   if (rc) return rc;
@@ -719,11 +768,6 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
   if (multi && (rc = nq_comm_allreduce(ctx, ctx->hdr_stage, NQMC_HDR_SIZE, st))) return rc;
   // walkers, log|psi|, E_L and the header are final after phase A: send them home on a side stream while the
   // reverse pass (phase B) runs on the caller's stream
-  if (!ctx->side_stream) {
-    NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-    NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_phase_a, cudaEventDisableTiming));
-    NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
-  }
   cudaStream_t sd = ctx->side_stream;
   NQMC_CUDA(cudaEventRecord(ctx->ev_phase_a, st));
   NQMC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_phase_a, 0));
@@ -734,12 +778,33 @@ int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float*
   NQMC_CUDA(cudaMemcpyAsync(e_l, ctx->e_scratch, w * f, cudaMemcpyDeviceToHost, sd));
   NQMC_CUDA(cudaMemcpyAsync(hdr, ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double), cudaMemcpyDeviceToHost, sd));
   NQMC_CUDA(cudaEventRecord(ctx->ev_side_done, sd));
+  ctx->host_step_issued = true;
   rc = nqmc_walker_step_b(ctx, ctx->r_soa, ctx->e_scratch, W, ctx->hdr_stage, ctx->gsum_stage, st_);
   if (rc) return rc;
   if (multi && (rc = nq_comm_allreduce(ctx, ctx->gsum_stage, ctx->sys.P, st))) return rc;
   NQMC_CUDA(cudaMemcpyAsync(gsum, ctx->gsum_stage, (size_t)ctx->sys.P * sizeof(double), cudaMemcpyDeviceToHost, st));
   NQMC_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_done, 0));   // the next call on this stream reuses the staging buffers
-  NQMC_CUDA(cudaStreamSynchronize(st));
+  NQMC_CUDA(cudaEventRecord(ctx->ev_all_done, st));
+  return NQMC_OK;
+}
+
+int nqmc_walker_step_host_wait(nqmc_ctx* ctx, int what) {
+  if (!ctx) return NQMC_ERR_ARG;
+  if (!ctx->host_step_issued) {
+    ctx->err = "nqmc_walker_step_host_wait: no nqmc_walker_step_host_async call to wait for";
+    return NQMC_ERR_STATE;
+  }
+  NQMC_CUDA(cudaSetDevice(ctx->device));
+  NQMC_CUDA(cudaEventSynchronize(what == NQMC_WAIT_PHASE_A ? ctx->ev_side_done : ctx->ev_all_done));
+  return NQMC_OK;
+}
+
+int nqmc_walker_step_host(nqmc_ctx* ctx, float* r_aos, float* logp, const float* normals_aos, const float* uniforms,
+                          uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, double* hdr,
+                          double* gsum, nqmc_stream st_) {
+  int rc = nqmc_walker_step_host_async(ctx, r_aos, logp, normals_aos, uniforms, seed, step, wid0, sigma, W, e_l, hdr, gsum, st_);
+  if (rc) return rc;
+  NQMC_CUDA(cudaStreamSynchronize(S(st_)));
   return NQMC_OK;
 }
 

@@ -130,6 +130,14 @@ struct nqmc_ctx {
   struct nq_comm* comm = nullptr;   // peer-memory communicator (nqmc_comm.cu); nullptr: single GPU or NCCL outside
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_phase_a = nullptr, ev_side_done = nullptr;
+  // pipelined host entry (nqmc_walker_step_host_upload / _async / _wait): the next step's walkers are uploaded into the
+  // second SoA buffer on up_stream while the reverse pass of the running step still reads r_soa
+  float* r_soa2 = nullptr;     // [3N][cap_w]
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t ev_upload = nullptr, ev_all_done = nullptr;
+  bool up_pending = false, host_step_issued = false;
+  const float* up_r = nullptr; const float* up_logp = nullptr; const float* up_nrm = nullptr; const float* up_uni = nullptr;
+  int64_t up_W = 0;
 };
 enum { NQ_PROF_EVAL1 = 0, NQ_PROF_EVAL5 = 1, NQ_PROF_BWD = 2, NQ_PROF_ASSEMBLE = 3, NQ_PROF_ACCEPT = 4, NQ_PROF_MISC = 5 };
 

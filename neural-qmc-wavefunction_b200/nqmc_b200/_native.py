@@ -28,6 +28,7 @@ EXPORTS = [
     "nqmc_leaf_info", "nqmc_set_params", "nqmc_set_params_host", "nqmc_aos_to_soa", "nqmc_soa_to_aos",
     "nqmc_log_psi", "nqmc_mh_step", "nqmc_local_energy", "nqmc_grad_accum", "nqmc_energy_stats",
     "nqmc_walker_step_a", "nqmc_walker_step_b", "nqmc_walker_step", "nqmc_walker_step_host",
+    "nqmc_walker_step_host_async", "nqmc_walker_step_host_wait", "nqmc_walker_step_host_upload",
     "nqmc_launch_count", "nqmc_rng_fill", "nqmc_profile", "nqmc_profile_read", "nqmc_ffma_peak", "nqmc_use_tensor_cores", "nqmc_get_params", "nqmc_get_params_host", "nqmc_adam_step",
     "nqmc_comm_create", "nqmc_comm_attach", "nqmc_comm_allreduce", "nqmc_comm_active", "nqmc_sample", "nqmc_blocked_stats",
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
@@ -88,6 +89,9 @@ def load_library():
     lib.nqmc_walker_step_b.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.nqmc_walker_step.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, vp, vp, vp, vp, vp]
     lib.nqmc_walker_step_host.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, vp, vp, vp, vp]
+    lib.nqmc_walker_step_host_async.argtypes = [vp, vp, vp, vp, vp, u64, u64, i64, f32, i64, vp, vp, vp, vp]
+    lib.nqmc_walker_step_host_wait.argtypes = [vp, C.c_int]
+    lib.nqmc_walker_step_host_upload.argtypes = [vp, vp, vp, vp, vp, i64]
     lib.nqmc_launch_count.argtypes = [vp]
     lib.nqmc_launch_count.restype = i64
     lib.nqmc_rng_fill.argtypes = [vp, u64, u64, i64, i64, vp, vp, vp]
@@ -570,6 +574,37 @@ class Context:
                                                    np_ptr(uniforms), int(seed) & (2**64 - 1), int(step), int(walker_id0),
                                                    float(sigma), W, e_l.ctypes.data, hdr.ctypes.data, gsum.ctypes.data,
                                                    self.stream), "nqmc_walker_step_host")
+
+    WAIT_PHASE_A, WAIT_ALL = 0, 1
+
+    def walker_step_host_async(self, r_aos: np.ndarray, logp: np.ndarray, sigma: float, e_l: np.ndarray, hdr: np.ndarray,
+                               gsum: np.ndarray, normals_aos: Optional[np.ndarray] = None,
+                               uniforms: Optional[np.ndarray] = None, seed=0, step=0, walker_id0=0):
+        """``walker_step_host`` without the final synchronisation; pair with ``walker_step_host_wait``.  The host arrays
+        must stay alive (and should be pinned) until the matching wait returns."""
+        W = r_aos.shape[0]
+        self.reserve(W)
+        np_ptr = lambda a: None if a is None else a.ctypes.data
+        self._check(self.lib.nqmc_walker_step_host_async(self.h, r_aos.ctypes.data, logp.ctypes.data, np_ptr(normals_aos),
+                                                         np_ptr(uniforms), int(seed) & (2**64 - 1), int(step),
+                                                         int(walker_id0), float(sigma), W, e_l.ctypes.data,
+                                                         hdr.ctypes.data, gsum.ctypes.data, self.stream),
+                    "nqmc_walker_step_host_async")
+
+    def walker_step_host_wait(self, what: int = 1):
+        """Block until the phase-A outputs (``WAIT_PHASE_A``: walkers, log|psi|^2, E_L, header) or everything
+        (``WAIT_ALL``: the gradient sums too) of the last ``walker_step_host_async`` is in the host arrays."""
+        self._check(self.lib.nqmc_walker_step_host_wait(self.h, int(what)), "nqmc_walker_step_host_wait")
+
+    def walker_step_host_upload(self, r_aos: np.ndarray, logp: np.ndarray, normals_aos: Optional[np.ndarray] = None,
+                                uniforms: Optional[np.ndarray] = None):
+        """Start copying the NEXT step's inputs to the device while the reverse pass of the running step executes
+        (call after ``walker_step_host_wait(WAIT_PHASE_A)``); the next host step that names the same arrays skips its copy."""
+        W = r_aos.shape[0]
+        self.reserve(W)
+        np_ptr = lambda a: None if a is None else a.ctypes.data
+        self._check(self.lib.nqmc_walker_step_host_upload(self.h, r_aos.ctypes.data, logp.ctypes.data, np_ptr(normals_aos),
+                                                          np_ptr(uniforms), W), "nqmc_walker_step_host_upload")
 
     # ---- multi-GPU: peer-memory communicator (include/nqmc_b200.h, "multi-GPU") ----
     COMM_HANDLE_BYTES = 64

@@ -287,3 +287,53 @@ def test_node_hit_is_counted_not_propagated():
     assert h[4] == 1 and h[0] == 255
     assert abs(h[1] - np.delete(e, 17).astype(np.float64).sum()) < 1e-6 * np.abs(np.delete(e, 17)).sum()
     assert np.isfinite(gsum.cpu().numpy()).all()
+
+
+@pytest.mark.gpu
+def test_pipelined_host_step_matches_synchronous_host_step():
+    """nqmc_walker_step_host_upload / _async / _wait (next step's walkers travel to the device during the reverse pass of
+    the running one) against the synchronous nqmc_walker_step_host: same walkers, log|psi|^2, E_L and header bit for bit,
+    gradient sums to summation order, over several chained steps; an unmatched upload is ignored."""
+    from _util import make_case, make_context
+    s, net, theta, r0 = make_case(n_atoms=4, hidden=64, W=777, burn=5)
+    ctx = make_context(s, net)
+    ctx.set_params(theta)
+    W = r0.shape[0]
+    _, la = ctx.log_psi(ctx.to_soa(r0))
+    logp0 = (2.0 * la.cpu().numpy()).astype(np.float32)
+    rng = np.random.default_rng(11)
+    n_steps = 4
+    normals = [rng.standard_normal(r0.shape).astype(np.float32) for _ in range(n_steps)]
+    uniforms = [rng.random(W).astype(np.float32) for _ in range(n_steps)]
+
+    def buffers():
+        return (np.ascontiguousarray(r0).copy(), logp0.copy(), np.empty(W, np.float32), np.empty(8, np.float64),
+                np.empty(ctx.P, np.float64))
+
+    for explicit in (True, False):
+        # synchronous reference
+        r_s, lp_s, e_s, h_s, g_s = buffers()
+        ref = []
+        for t in range(n_steps):
+            kw = dict(normals_aos=normals[t], uniforms=uniforms[t]) if explicit else dict(seed=5, step=100 + t)
+            ctx.walker_step_host(r_s, lp_s, 0.3, e_s, h_s, g_s, **kw)
+            ref.append((r_s.copy(), lp_s.copy(), e_s.copy(), h_s.copy(), g_s.copy()))
+        # pipelined
+        r_p, lp_p, e_p, h_p, g_p = buffers()
+        junk = np.zeros_like(r_p)
+        ctx.walker_step_host_upload(junk, lp_p)                      # names other arrays: must not be picked up
+        for t in range(n_steps):
+            kw = dict(normals_aos=normals[t], uniforms=uniforms[t]) if explicit else dict(seed=5, step=100 + t)
+            ctx.walker_step_host_async(r_p, lp_p, 0.3, e_p, h_p, g_p, **kw)
+            ctx.walker_step_host_wait(ctx.WAIT_PHASE_A)
+            got_a = (r_p.copy(), lp_p.copy(), e_p.copy(), h_p.copy())
+            if t + 1 < n_steps:                                      # next step's inputs travel during the reverse pass
+                if explicit:
+                    ctx.walker_step_host_upload(r_p, lp_p, normals[t + 1], uniforms[t + 1])
+                else:
+                    ctx.walker_step_host_upload(r_p, lp_p)
+            ctx.walker_step_host_wait(ctx.WAIT_ALL)
+            for a, b in zip(got_a, ref[t][:4]):
+                assert np.array_equal(a, b), (explicit, t)
+            assert np.allclose(g_p, ref[t][4], rtol=1e-5, atol=1e-5 * np.abs(ref[t][4]).max()), (explicit, t)
+    ctx.synchronize()
