@@ -53,6 +53,22 @@ struct DevSys {     // passed by value to kernels (<= 4 KB kernel-parameter budg
 };
 
 // entry index of (spin, electron-in-spin i, orbital k) in the orbital scratch
+// Work items of the persistent orbital kernels are (walker block wb, electron-of-spin e) pairs numbered wb * ns + e and
+// dealt round-robin: CTA `first`, then first + stride, ...  The decomposition is advanced incrementally -- one division
+// per thread at kernel start instead of a 64-bit div + mod per tile (which cost ~60 instructions of a ~500-instruction
+// tile in the value kernel).  The launchers check that the item count fits 31 bits.
+struct ItemIter {
+  int wb, e, dq, dr, ns;
+  __host__ __device__ ItemIter(int first, int stride, int ns_) : ns(ns_) {
+    wb = first / ns_; e = first - wb * ns_;
+    dq = stride / ns_; dr = stride - dq * ns_;
+  }
+  __host__ __device__ void next() {
+    wb += dq; e += dr;
+    if (e >= ns) { e -= ns; ++wb; }
+  }
+};
+
 __host__ __device__ inline int ent_index(const DevSys& s, int spin, int i, int k) {
   return spin == 0 ? i * s.n_up + k : s.n_up * s.n_up + i * s.n_dn + k;
 }

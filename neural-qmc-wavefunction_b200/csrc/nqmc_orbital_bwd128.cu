@@ -385,9 +385,10 @@ __global__ void __launch_bounds__(SEED_T, 1)
   // second role in the summing phase: thread (unit = tid % 128, part = tid / 128) adds rows 16 part .. 16 part + 15
   float acc = 0.f, accb = 0.f;
   const int64_t n_items = nwb * ns;
-  for (int64_t item = chunk; item < n_items; item += n_chunks) {
-    const int64_t w = (item / ns) * ROWS + row;
-    const int i = (int)(item % ns);
+  ItemIter cur(chunk, n_chunks, ns);
+  for (int64_t item = chunk; item < n_items; item += n_chunks, cur.next()) {
+    const int64_t w = (int64_t)cur.wb * ROWS + row;
+    const int i = cur.e;
     const int64_t base = ((int64_t)m * H + SEED_U * grp) * rows_pad + item * ROWS + row;
     float h2[SEED_U];
 #pragma unroll

@@ -369,9 +369,11 @@ __global__ void __launch_bounds__(TCT, 1)
   // register prefetch was spilled by ptxas, and a spilled load stalls on the spot), waits for them at the end of P3
   // and the tile barrier there publishes them to the row's four threads.
   float* pf = reinterpret_cast<float*>(smem + mp.pf);            // [5][ROWS]
-  auto fetch = [&](const int64_t item) {
-    const int i = (int)(item % ns);
-    int64_t w = (item / ns) * ROWS + row;
+  ItemIter cur(chunk, n_chunks, ns), nxt = cur;                 // this tile / the next tile to request (in order)
+  auto fetch = [&]() {
+    const int i = nxt.e;
+    int64_t w = (int64_t)nxt.wb * ROWS + row;
+    nxt.next();
     if (w >= W) w = W - 1;
     const int e = elec0 + i;
     const float* src[5] = {r + (int64_t)(3 * e + 0) * W + w, r + (int64_t)(3 * e + 1) * W + w, r + (int64_t)(3 * e + 2) * W + w,
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(TCT, 1)
   };
   if (worker && chunk < n_items) {
     if (quarter == 0) {
-      fetch(chunk);
+      fetch();
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
     asm volatile("bar.sync 2, %0;" ::"n"(TCW) : "memory");      // workers only
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(TCT, 1)
     }
   }
   int64_t n_done = 0;                                  // tiles this CTA has completed
-  for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done) {
+  for (int64_t item = chunk; item < n_items; item += n_chunks, ++n_done, cur.next()) {
     float h1[UPT], d2[UPT], seed = 0.f;
     // ======== P1 ========
     if (worker) {
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(TCT, 1)
         float wt = nwt;
         if (wgt == nullptr && e_l != nullptr) wt = isfinite(nwt) ? nwt - centerf : 0.f;
         seed = wt * ninv;
-        if ((item / ns) * ROWS + row >= W || !isfinite(seed)) seed = 0.f;
+        if ((int64_t)cur.wb * ROWS + row >= W || !isfinite(seed)) seed = 0.f;
       }
       if constexpr (L1TC) {
         // P0: this thread's share of the row's features -> TMEM (operand order x, y, z, 1, (d_a, e_a) pairs) and -> fstage
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(TCT, 1)
     // ======== P3 ========
     if (worker) {
       const bool more = item + n_chunks < n_items;
-      if (more && quarter == 0) fetch(item + n_chunks);         // next tile's positions / seed (read last in P1, two barriers ago)
+      if (more && quarter == 0) fetch();         // next tile's positions / seed (read last in P1, two barriers ago)
       if (n_done > 0) { mbar_wait(bar_g, ph_g); ph_g ^= 1; }   // G1(t-1) reads delta1^T(t-1) and the features of tile t-1
       stage_mn(dM_hi, dM_lo, mn_off0, mn_off1, d2, mn_flip);
       // granule (feature unit f, row group g) <- fstage[f][4g .. 4g+3]

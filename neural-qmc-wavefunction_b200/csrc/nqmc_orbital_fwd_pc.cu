@@ -301,22 +301,24 @@ __global__ void __launch_bounds__(TCT, 1)
     float gb3 = 0.f;
 #pragma unroll
     for (int j = 0; j < (BW ? C::EPC : 1); ++j) gW3[j] = 0.f;
-    auto fetch = [&](const int64_t item) {
-      int64_t w = (item / ns) * ROWS + row;
+    ItemIter cur(chunk, n_chunks, ns), nxt = cur;             // this tile / the next tile to request (in order)
+    auto fetch = [&]() {
+      int64_t w = (int64_t)nxt.wb * ROWS + row;
       if (w >= W) w = W - 1;
-      const int e = elec0 + (int)(item % ns);
+      const int e = elec0 + nxt.e;
       nx = r[(int64_t)(3 * e + 0) * W + w];
       ny = r[(int64_t)(3 * e + 1) * W + w];
       nz = r[(int64_t)(3 * e + 2) * W + w];
       if constexpr (BW) {
         nwt = bw.wgt != nullptr ? bw.wgt[w] : (bw.e_l != nullptr ? bw.e_l[w] : 1.0f);
-        ninv = bw.inv[(int64_t)ent_index(s, spin, (int)(item % ns), korb) * W + w];
+        ninv = bw.inv[(int64_t)ent_index(s, spin, nxt.e, korb) * W + w];
       }
+      nxt.next();
     };
-    if (chunk < n_items) fetch(chunk);
-    for (int64_t item = chunk; item < n_items; item += n_chunks, ++tl) {
-      const int i = (int)(item % ns);
-      const int64_t w0 = (item / ns) * ROWS;
+    if (chunk < n_items) fetch();
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++tl, cur.next()) {
+      const int i = cur.e;
+      const int64_t w0 = (int64_t)cur.wb * ROWS;
       const float x = nx, y = ny, z = nz;
       float seed = 0.f;
       if constexpr (BW) {
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(TCT, 1)
         if (w0 + row >= W || !isfinite(seed)) seed = 0.f;
       }
       const int64_t rid = item * ROWS + row;                   // BW: row id inside this network's scratch arrays
-      if (item + n_chunks < n_items) fetch(item + n_chunks);
+      if (item + n_chunks < n_items) fetch();
       // per nucleus: d, exp(-d), unit vector, 2/d.  With s = wd - e we the five channels of (d, e) contribute
       //   value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we      (7 FMA per nucleus and unit, not 10)
       // GW: Laplacian-channel inputs become  L_G d = (tr G - u^T G u)/d =: A ,  L_G e^-d = e (q - A) with q = u^T G u

@@ -201,13 +201,15 @@ __global__ void __launch_bounds__(TCT, 1)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t g = 0, t = 0;
     float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
-    auto fetch = [&](const int64_t item) {
-      int64_t w = (item / ns) * ROWS + row;
+    ItemIter cur(chunk, n_chunks, ns), nxt = cur;             // this tile / the next tile whose positions are requested
+    auto fetch = [&]() {                                       // tiles are requested in order: chunk, chunk + n_chunks, ...
+      int64_t w = (int64_t)nxt.wb * ROWS + row;
       if (w >= W) w = W - 1;
-      const int e = elec0 + (int)(item % ns);
+      const int e = elec0 + nxt.e;
       nx = r[(int64_t)(3 * e + 0) * W + w];
       ny = r[(int64_t)(3 * e + 1) * W + w];
       nz = r[(int64_t)(3 * e + 2) * W + w];
+      nxt.next();
     };
     // per nucleus: d, exp(-d), unit vector, 2/d -- in registers for all 8 chunks.  With s = wd - e we the five
     // channels of (d, e) contribute  value: d wd + e we ; gradient: u s ; Laplacian: (2/d) s + e we   (7 FMA, not 10).
@@ -227,18 +229,18 @@ __global__ void __launch_bounds__(TCT, 1)
     // epilogue: 6 registers per nucleus, which the 112-register budget has room for up to 4 nuclei)
     constexpr bool AHEAD = NA <= 4;
     if (chunk < n_items) {
-      fetch(chunk);
+      fetch();
       if (AHEAD) {
         features();
-        if (chunk + n_chunks < n_items) fetch(chunk + n_chunks);
+        if (chunk + n_chunks < n_items) fetch();
       }
     }
-    for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
-      const int i = (int)(item % ns);
-      const int64_t w0 = (item / ns) * ROWS;
+    for (int64_t item = chunk; item < n_items; item += n_chunks, ++t, cur.next()) {
+      const int i = cur.e;
+      const int64_t w0 = (int64_t)cur.wb * ROWS;
       if (!AHEAD) {
         features();
-        if (item + n_chunks < n_items) fetch(item + n_chunks);
+        if (item + n_chunks < n_items) fetch();
       }
 #pragma unroll 2
       for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(TCT, 1)
       // tile's) fill the wait, and the positions of the tile after that are requested
       if (AHEAD && item + n_chunks < n_items) {
         features();
-        if (item + 2 * (int64_t)n_chunks < n_items) fetch(item + 2 * (int64_t)n_chunks);
+        if (item + 2 * (int64_t)n_chunks < n_items) fetch();
       }
       // ---- epilogue ------------------------------------------------------------------------------------------
       mbar_wait(dfull, t & 1);
@@ -374,6 +376,7 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, cudaStream_t 
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
+  if (max_items >= (int64_t)1 << 31) return NQMC_ERR_UNSUPPORTED;   // ItemIter counts items in 32 bits
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;

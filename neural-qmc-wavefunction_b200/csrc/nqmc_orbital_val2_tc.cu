@@ -232,23 +232,23 @@ __global__ void __launch_bounds__(TCT, 1)
   asm volatile("bar.sync 2, %0;" ::"n"(TCW) : "memory");        // workers only: zeros before the first features
   uint32_t ph_l1[2] = {0u, 0u}, ph_u[2] = {0u, 0u};
   float nx = 0.f, ny = 0.f, nz = 0.f;                           // positions of the tile whose features are written next step
-  auto item_of = [&](const int64_t t) { return chunk + t * (int64_t)n_chunks; };
-  auto fetch = [&](const int64_t t) {
-    const int64_t it = item_of(t);
-    int64_t w = (it / ns) * ROWS + row;
+  ItemIter it_f(chunk, n_chunks, ns), it_c = it_f;              // next tile to fetch / tile whose phi is stored next
+  auto fetch = [&]() {                                          // tiles are requested in order: 0, 1, 2, ...
+    int64_t w = (int64_t)it_f.wb * ROWS + row;
     if (w >= W) w = W - 1;
-    const int e = elec0 + (int)(it % ns);
+    const int e = elec0 + it_f.e;
     nx = r[(int64_t)(3 * e + 0) * W + w];
     ny = r[(int64_t)(3 * e + 1) * W + w];
     nz = r[(int64_t)(3 * e + 2) * W + w];
+    it_f.next();
   };
-  if (n_tiles > 0) fetch(0);
+  if (n_tiles > 0) fetch();
 #pragma unroll 2
   for (int64_t st = -2; st < n_tiles; ++st) {
     // ---- W_a: features of tile st+2 -> FA[(st+2)&1].  Quarter q takes nuclei q, q+4, ..; quarter 0 also x, y, z, 1.
     if (st + 2 < n_tiles) {
       const float x = nx, y = ny, z = nz;
-      if (st + 3 < n_tiles) fetch(st + 3);
+      if (st + 3 < n_tiles) fetch();
       const uint32_t fa = tmem_base + lane_base + C_FA + 32u * (uint32_t)((st + 2) & 1);
       if (quarter == 0) {                                       // columns 0..3: x, y, z, 1 (the ones column carries b1)
         uint32_t h0, l0, h1, l1, h2, l2;
@@ -309,15 +309,17 @@ __global__ void __launch_bounds__(TCT, 1)
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // feature and h1 stores of this step
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tile_barrier();        // FA(st+2), A2(st+1) complete; D1/U2 of tile st read; partial outputs visible
-    if (st >= 0 && quarter == 0) {
-      const int64_t it = item_of(st);
-      const int64_t wr = (it / ns) * ROWS + row;
-      if (wr < W) {
-        float o = out + b3;
+    if (st >= 0) {
+      if (quarter == 0) {
+        const int64_t wr = (int64_t)it_c.wb * ROWS + row;
+        if (wr < W) {
+          float o = out + b3;
 #pragma unroll
-        for (int q = 0; q < NQ - 1; ++q) o += outS[(pb * (NQ - 1) + q) * ROWS + row];
-        phi[(int64_t)ent_index(s, spin, (int)(it % ns), korb) * W + wr] = o;
+          for (int q = 0; q < NQ - 1; ++q) o += outS[(pb * (NQ - 1) + q) * ROWS + row];
+          phi[(int64_t)ent_index(s, spin, it_c.e, korb) * W + wr] = o;
+        }
       }
+      it_c.next();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -341,6 +343,7 @@ int nq_launch_orb_eval1_l1tc(nqmc_ctx* ctx, const float* r, int64_t W, float* ph
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
+  if (max_items >= (int64_t)1 << 31) return NQMC_ERR_UNSUPPORTED;   // ItemIter counts items in 32 bits
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
