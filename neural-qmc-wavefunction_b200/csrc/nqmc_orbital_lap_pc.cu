@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(TCT, 1)
     const int iw = warp - NWW;                                 // channel c is issued by warp c % NISS
     const uint32_t leader = elect_one();
     const uint64_t dBh = umma_desc(smem_u32(Bhi), B_K4, 128), dBl = umma_desc(smem_u32(Blo), B_K4, 128);
-    uint32_t g = 0, t = 0;                                     // global chunk counter, local tile counter
+    uint32_t t = 0;                                            // local tile counter (global chunk number = 8 t + kc)
     for (int64_t item = chunk; item < n_items; item += n_chunks, ++t) {
       if (t > 0) mbar_wait(dempty, (t - 1) & 1);               // accumulators of the previous tile have been read
 #pragma unroll 8
-      for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
-        const uint32_t b = g & 1, u = g >> 1;
-        mbar_wait(full0 + 8 * b, u & 1);
+      for (int kc = 0; kc < NCHUNK; ++kc) {
+        const uint32_t b = kc & 1;
+        mbar_wait(full0 + 8 * b, (kc >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t kb = (uint64_t)(((uint32_t)kc * 2 * B_K4) >> 4);
         const uint32_t abase = tmem_base + C_A + A_STRIDE * b;
@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(TCT, 1)
     // =============================== worker warps ========================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t g = 0, t = 0;
+    const uint32_t t_q = tmem_base + lane_base + C_A + (uint32_t)(UPT * quarter);
+    const float* const w1q = W1s + UPT * quarter;
+    const float* const b1q = b1s + UPT * quarter;
+    uint32_t t = 0;
     float nx = 0.f, ny = 0.f, nz = 0.f;                        // positions of the next tile, fetched one tile ahead
     ItemIter cur(chunk, n_chunks, ns), nxt = cur;             // this tile / the next tile whose positions are requested
     auto fetch = [&]() {                                       // tiles are requested in order: chunk, chunk + n_chunks, ...
@@ -242,9 +245,14 @@ __global__ void __launch_bounds__(TCT, 1)
         features();
         if (item + n_chunks < n_items) fetch();
       }
-#pragma unroll 2
-      for (int kc = 0; kc < NCHUNK; ++kc, ++g) {
-        const int j0 = KC * kc + UPT * quarter;
+      // fully unrolled: the global chunk number is 8 t + kc, so the staging buffer (kc & 1), both mbarrier parities and
+      // every shared-memory / TMEM offset of a chunk are immediates (the 2x-unrolled loop spent ~20 of its 126
+      // instructions per chunk re-deriving them from threadIdx)
+#pragma unroll
+      for (int kc = 0; kc < NCHUNK; ++kc) {
+        const float* W1s = w1q + KC * kc;                       // shadows the CTA-wide pointers: this thread's two units
+        const float* b1s = b1q + KC * kc;
+        constexpr int j0 = 0;
         // the thread's two hidden units are one packed pair: every FMA / MUL / ADD below is one FFMA2 / FMUL2 / FADD2
         float2 acc[CH];
         {
@@ -279,9 +287,9 @@ __global__ void __launch_bounds__(TCT, 1)
           acc[3] = nq_mul2(acc[3], tp);
           acc[0] = h;
         }
-        const uint32_t b = g & 1, u = g >> 1;
-        if (u > 0) mbar_wait(empty0 + 8 * b, (u - 1) & 1);      // MMAs of the previous use of this buffer are done
-        const uint32_t t_hi = tmem_base + lane_base + C_A + A_STRIDE * b + (uint32_t)(UPT * quarter);
+        const uint32_t b = kc & 1;                              // u = (8 t + kc) >> 1 uses of this buffer so far
+        if (t > 0 || kc >= 2) mbar_wait(empty0 + 8 * b, ((kc >> 1) + 1) & 1);   // MMAs of its previous use are done
+        const uint32_t t_hi = t_q + A_STRIDE * b;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const float2 hi = make_float2(__uint_as_float(__float_as_uint(acc[c].x) & 0xFFFFE000u),
