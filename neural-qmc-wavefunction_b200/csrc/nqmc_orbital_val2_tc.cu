@@ -18,6 +18,9 @@
 
 #include "nqmc_internal.cuh"
 
+#ifndef NQMC_EVAL1_STAGGER
+#define NQMC_EVAL1_STAGGER 1
+#endif
 namespace {
 
 constexpr int H = 64;
@@ -100,7 +103,7 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 
 __global__ void __launch_bounds__(TCT, 1)
     orb_eval1_l1tc_kernel(const DevSys s, const float* __restrict__ theta, const float* __restrict__ r, const int64_t W,
-                          float* __restrict__ phi, const int n_chunks) {
+                          float* __restrict__ phi, const int n_chunks, const int order) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* W2hi = smem;                                  // [k/4][n][k%4]
   uint8_t* W2lo = W2hi + W2B;
@@ -246,7 +249,14 @@ __global__ void __launch_bounds__(TCT, 1)
 #pragma unroll 2
   for (int64_t st = -2; st < n_tiles; ++st) {
     // ---- W_a: features of tile st+2 -> FA[(st+2)&1].  Quarter q takes nuclei q, q+4, ..; quarter 0 also x, y, z, 1.
-    if (st + 2 < n_tiles) {
+    // The three work items of a step touch different tiles and are independent.  The four warps that share an SM
+    // sub-partition (the four quarters of 32 rows) leave the step barrier together; if all of them run a, b, c they
+    // send their MUFU batches (2 per tanh) to the sub-partition's one XU pipe at the same moment and then all run their
+    // FP32 work while it idles.  Odd quarters therefore run b, a, c: half of the warps are in the feature stage while
+    // the other half use the XU pipe (value kernel 63.7 -> 58 us).
+    const int a_pos = (order >> (2 * quarter)) & 3;             // 0: a, b, c   1: b, a, c   2: b, c, a
+    auto stage_a = [&]() {
+      if (!(st + 2 < n_tiles)) return;
       const float x = nx, y = ny, z = nz;
       if (st + 3 < n_tiles) fetch();
       const uint32_t fa = tmem_base + lane_base + C_FA + 32u * (uint32_t)((st + 2) & 1);
@@ -267,7 +277,8 @@ __global__ void __launch_bounds__(TCT, 1)
         tmem_st2(fa + (uint32_t)(4 + 2 * a), h0, h1);
         tmem_st2(fa + (uint32_t)(K1 + 4 + 2 * a), l0, l1);
       }
-    }
+    };
+    if (a_pos == 0) stage_a();
     // ---- W_b: h1 = tanh(D1) of tile st+1 -> A2[(st+1)&1]
     if (st + 1 >= 0 && st + 1 < n_tiles) {
       const uint32_t b = (uint32_t)((st + 1) & 1);
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(TCT, 1)
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)c0, hi);
       tmem_st16(tmem_base + lane_base + C_A2 + 128u * b + (uint32_t)(H + c0), lo);
     }
+    if (a_pos == 1) stage_a();
     // ---- W_c: phi of tile st
     float out = 0.f;
     const uint32_t pb = (uint32_t)(st & 1);
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(TCT, 1)
       out = o2.x + o2.y;
       if (quarter != 0) outS[(pb * (NQ - 1) + quarter - 1) * ROWS + row] = out;
     }
+    if (a_pos >= 2) stage_a();
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // feature and h1 stores of this step
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tile_barrier();        // FA(st+2), A2(st+1) complete; D1/U2 of tile st read; partial outputs visible
@@ -349,8 +362,11 @@ int nq_launch_orb_eval1_l1tc(nqmc_ctx* ctx, const float* r, int64_t W, float* ph
   if (n_chunks > max_items) n_chunks = (int)max_items;
   {
     ProfScope ps(ctx, NQ_PROF_EVAL1, st);
-    if (ctx->prof_on) orb_eval1_l1tc_kernel<<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks);
-    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_eval1_l1tc_kernel, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks));
+    // stage order per quarter, 2 bits each (see the kernel); default 0x60: quarters 0, 1: a, b, c; quarter 2: b, c, a;
+    // quarter 3: b, a, c (scripts/exp/sweep_eval1_order.py: 65.7 us unstaggered, 57.9 - 59.9 us for every staggered setting)
+    static const int order = [] { const char* e = getenv("NQMC_EVAL1_ORDER"); return e ? (int)strtol(e, nullptr, 0) : 0x60; }();
+    if (ctx->prof_on) orb_eval1_l1tc_kernel<<<n_chunks * s.n_mlp, TCT, smem, st>>>(s, ctx->theta, r, W, phi, n_chunks, order);
+    else NQMC_CUDA(nq_launch_pdl_guarded(ctx, orb_eval1_l1tc_kernel, dim3(n_chunks * s.n_mlp), dim3(TCT), smem, st, s, ctx->theta, r, W, phi, n_chunks, order));
   }
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;
