@@ -269,6 +269,7 @@ int nqmc_destroy(nqmc_ctx* ctx) {
   nq_comm_free(ctx);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
+  if (ctx->ev_mh_done) cudaEventDestroy(ctx->ev_mh_done);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
   if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
@@ -550,7 +551,14 @@ int nqmc_local_energy(nqmc_ctx* ctx, const float* r, int64_t W, float* e_l, floa
 // reverse pass given that ctx->inv already holds the inverse orbital matrices for r
 static int grads_core(nqmc_ctx* ctx, const float* r, const float* wgt, const double* hdr, const float* e_l, int64_t W,
                       double* out, cudaStream_t st) {
-  NQMC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)ctx->sys.P, st));
+  // Plain Slater-Jastrow inside the fused step: orb_bwd_reduce_kernel assigns every network entry and
+  // jastrow_from_sums_kernel the four Jastrow scalars -- all P entries -- so the clear is skipped there (it would also sit
+  // between the statistics kernel and the reverse-pass kernel and defeat the programmatic dependent launch of the latter).
+  const DevSys& sy = ctx->sys;
+  const bool all_assigned = sy.kind == NQMC_KIND_ANTISYMMETRIC && !sy.use_cusp && !sy.use_bf && wgt == nullptr &&
+                            hdr != nullptr && e_l != nullptr && ctx->jas_valid_for == e_l &&
+                            (int64_t)sy.P == (int64_t)sy.n_mlp * ctx->p_mlp + 4;
+  if (!all_assigned) NQMC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)ctx->sys.P, st));
   if (ctx->sys.kind == NQMC_KIND_SIMPLE) return nq_simple_grads(ctx, r, wgt, hdr, e_l, W, out, st);
   int rc = nq_launch_orb_bwd(ctx, ctx->sys.use_bf ? ctx->x_cur : r, wgt, hdr, e_l, W, out, st);
   if (rc) return rc;
@@ -615,6 +623,10 @@ int nqmc_blocked_stats(nqmc_ctx* ctx, const float* e_l, int64_t n_samples, int64
   return nq_blocked_stats(ctx, e_l, n_samples, W, n_blocks, out3, S(st));
 }
 
+// Phase A = the MH move (after which the walkers and log|psi|^2 are final) + the energy pass.  The host-buffer entry point
+// starts sending the walkers home between the two.
+static int step_a_energy(nqmc_ctx* ctx, float* r, int64_t W, float* e_l, double* hdr, nqmc_stream st);
+
 int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normals, const float* uniforms,
                        uint64_t seed, uint64_t step, int64_t wid0, float sigma, int64_t W, float* e_l, float* n_acc,
                        double* hdr, nqmc_stream st) {
@@ -624,6 +636,11 @@ int nqmc_walker_step_a(nqmc_ctx* ctx, float* r, float* logp, const float* normal
   NQMC_CUDA(cudaSetDevice(ctx->device));
   rc = mh_core(ctx, r, logp, normals, uniforms, seed, step, wid0, sigma, W, nullptr, n_acc, S(st));
   if (rc) return rc;
+  return step_a_energy(ctx, r, W, e_l, hdr, st);
+}
+
+static int step_a_energy(nqmc_ctx* ctx, float* r, int64_t W, float* e_l, double* hdr, nqmc_stream st) {
+  int rc;
   ctx->jas_valid_for = nullptr;
   ctx->act_valid_for = nullptr;
   ctx->act_stored = false;
@@ -698,6 +715,7 @@ int host_streams(nqmc_ctx* ctx) {
   NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   NQMC_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
   NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_phase_a, cudaEventDisableTiming));
+  NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_mh_done, cudaEventDisableTiming));
   NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
   NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
   NQMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_all_done, cudaEventDisableTiming));
@@ -761,20 +779,26 @@ int nqmc_walker_step_host_async(nqmc_ctx* ctx, float* r_aos, float* logp, const 
   if (!staged && (rc = stage_inputs(ctx, r_aos, logp, normals_aos, uniforms, W, ctx->r_soa, st))) return rc;
   const float* nrm = normals_aos ? ctx->nrm_soa : nullptr;
   const float* uni = uniforms ? ctx->uni_stage : nullptr;
-  rc = nqmc_walker_step_a(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, ctx->e_scratch, nullptr,
-                          ctx->hdr_stage, st_);
+  rc = mh_core(ctx, ctx->r_soa, ctx->logp_stage, nrm, uni, seed, step, wid0, sigma, W, nullptr, nullptr, st);
+  if (rc) return rc;
+  // The walkers and log|psi|^2 are final after the MH move, E_L and the header after the energy pass: they go home on a
+  // side stream while the energy pass and the reverse pass run on the caller's stream.  The SoA -> AoS conversion stays on
+  // the caller's stream: the persistent tensor-core kernels that follow fill every SM (the reverse pass holds all 227 KB
+  // of shared memory, and programmatic dependent launch makes it resident before its predecessor ends), so a conversion
+  // kernel on the side stream would only get its turn after them -- only the copy engines run beside them.
+  cudaStream_t sd = ctx->side_stream;
+  rc = nq_aos_soa(ctx, ctx->r_soa, ctx->aos_stage, W, false, st);
+  if (rc) return rc;
+  NQMC_CUDA(cudaEventRecord(ctx->ev_mh_done, st));
+  NQMC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_mh_done, 0));
+  NQMC_CUDA(cudaMemcpyAsync(r_aos, ctx->aos_stage, nn * w * f, cudaMemcpyDeviceToHost, sd));
+  NQMC_CUDA(cudaMemcpyAsync(logp, ctx->logp_stage, w * f, cudaMemcpyDeviceToHost, sd));
+  rc = step_a_energy(ctx, ctx->r_soa, W, ctx->e_scratch, ctx->hdr_stage, st_);
   if (rc) return rc;
   const bool multi = nq_comm_active(ctx);
   if (multi && (rc = nq_comm_allreduce(ctx, ctx->hdr_stage, NQMC_HDR_SIZE, st))) return rc;
-  // walkers, log|psi|, E_L and the header are final after phase A: send them home on a side stream while the
-  // reverse pass (phase B) runs on the caller's stream
-  cudaStream_t sd = ctx->side_stream;
   NQMC_CUDA(cudaEventRecord(ctx->ev_phase_a, st));
   NQMC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_phase_a, 0));
-  rc = nq_aos_soa(ctx, ctx->r_soa, ctx->aos_stage, W, false, sd);
-  if (rc) return rc;
-  NQMC_CUDA(cudaMemcpyAsync(r_aos, ctx->aos_stage, nn * w * f, cudaMemcpyDeviceToHost, sd));
-  NQMC_CUDA(cudaMemcpyAsync(logp, ctx->logp_stage, w * f, cudaMemcpyDeviceToHost, sd));
   NQMC_CUDA(cudaMemcpyAsync(e_l, ctx->e_scratch, w * f, cudaMemcpyDeviceToHost, sd));
   NQMC_CUDA(cudaMemcpyAsync(hdr, ctx->hdr_stage, NQMC_HDR_SIZE * sizeof(double), cudaMemcpyDeviceToHost, sd));
   NQMC_CUDA(cudaEventRecord(ctx->ev_side_done, sd));

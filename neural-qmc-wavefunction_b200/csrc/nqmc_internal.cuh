@@ -145,7 +145,7 @@ struct nqmc_ctx {
   // host entry point: results of phase A travel back on a side stream while phase B (the reverse pass) runs
   struct nq_comm* comm = nullptr;   // peer-memory communicator (nqmc_comm.cu); nullptr: single GPU or NCCL outside
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_phase_a = nullptr, ev_side_done = nullptr;
+  cudaEvent_t ev_phase_a = nullptr, ev_side_done = nullptr, ev_mh_done = nullptr;
   // pipelined host entry (nqmc_walker_step_host_upload / _async / _wait): the next step's walkers are uploaded into the
   // second SoA buffer on up_stream while the reverse pass of the running step still reads r_soa
   float* r_soa2 = nullptr;     // [3N][cap_w]
