@@ -42,6 +42,12 @@ __device__ __forceinline__ void ld_sys_v2u64(const unsigned long long* p, unsign
 __global__ void __launch_bounds__(256) allreduce_f64_kernel(double* __restrict__ vec, const int64_t len, const CommDev c,
                                                             const unsigned long long epoch, const long long budget,
                                                             int* __restrict__ timeout_flag) {
+  // The kernel behind the header exchange is the persistent reverse-pass kernel, launched with programmatic stream
+  // serialisation: let it become resident and stage its weights while this kernel waits for the peers (it reads the
+  // header only after griddepcontrol.wait, i.e. after this grid has completed and flushed).
+  nq_pdl_trigger();
+  // ... and this kernel is itself launched that way behind the statistics / Jastrow kernel that produces `vec`
+  nq_pdl_wait();
   const int par = (int)(epoch & 1ull);
   const long long t_start = clock64();
   const unsigned long long tag = ((epoch + 1ull) & 0xffffffffull) << 32;
@@ -175,7 +181,7 @@ int nq_comm_allreduce(nqmc_ctx* ctx, double* vec, int64_t len, cudaStream_t st) 
   if (n_cta > MAX_CTA) n_cta = MAX_CTA;
   int* flag_dev = nullptr;
   NQMC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flag_dev), c->timeout_flag, 0));
-  allreduce_f64_kernel<<<n_cta, 256, 0, st>>>(vec, len, d, c->epoch, c->budget_cycles, flag_dev);
+  NQMC_CUDA(nq_launch_pdl(allreduce_f64_kernel, dim3(n_cta), dim3(256), 0, st, vec, len, d, c->epoch, c->budget_cycles, flag_dev));
   c->epoch++;
   NQMC_LAUNCH_CHECK();
   return NQMC_OK;

@@ -362,6 +362,7 @@ __global__ void stats13_finish_kernel(const double* __restrict__ part, const int
 // out[jastrow scalar] = sum E O - Ebar sum O   with Ebar from the (all-reduced) header
 __global__ void jastrow_from_sums_kernel(const DevSys s, const double* __restrict__ jas, const double* __restrict__ hdr,
                                          double* __restrict__ out) {
+  nq_pdl_trigger();                                    // multi-GPU: the gradient exchange behind this kernel may get resident
   const int q = threadIdx.x;
   if (q >= 4) return;
   const double ebar = hdr[NQMC_HDR_SUM_E] / fmax(hdr[NQMC_HDR_N], 1.0);
