@@ -561,8 +561,8 @@ def run_ours(args):
                                          "frac_vs_sustained_peak": whole_tflops / (tf32_rec["sustained_tflops"] / 3.0),
                                          "note": "algorithmic flops of the whole fused walker step (SURVEY 8(d), 2mE(3+c)) over "
                                                  "its device time, against the same tensor denominator"},
-                          "traffic": 3.2609e6, "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum "
-                          "from the ncu --set full capture in profiles/r2f_ncu_full_metrics.txt (3.26 MB read = the walker positions, "
+                          "traffic": 3.2735e6, "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum "
+                          "from the ncu --set full capture in profiles/r2s_ncu_full_metrics.txt (3.27 MB read = the walker positions, "
                           "0 written: the 10.5 MB of orbital channels stay in the 126 MB L2 for the next kernel)",
                           "frac_of_mixed_floor": (t_floor / (ms5 / max(n5, 1) * 1e-3)) if n5 else None,
                           "mixed_floor_note": "floor = HxH-layer flops / (tf32/3) + other-layer flops / measured FFMA peak",
