@@ -18,9 +18,6 @@
 
 #include "nqmc_internal.cuh"
 
-#ifndef NQMC_EVAL1_STAGGER
-#define NQMC_EVAL1_STAGGER 1
-#endif
 namespace {
 
 constexpr int H = 64;
