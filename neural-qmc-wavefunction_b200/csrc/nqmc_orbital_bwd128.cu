@@ -457,6 +457,7 @@ int nq_launch_orb_bwd128(nqmc_ctx* ctx, const float* r, const float* wgt, const 
   const int64_t rows_pad = ctx->bw_rows;
   if (nq_bwd128_rows(ctx, W) > rows_pad) return NQMC_ERR_STATE;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
+  if (max_items >= (int64_t)1 << 31) return NQMC_ERR_UNSUPPORTED;   // ItemIter counts items in 32 bits
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks * s.n_mlp > ctx->n_cta_bwd) n_chunks = ctx->n_cta_bwd / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;

@@ -701,6 +701,7 @@ int launch_t(nqmc_ctx* ctx, const float* r, int64_t W, float* phi, const float* 
   }
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t max_items = nwb * (s.n_up > s.n_dn ? s.n_up : s.n_dn);
+  if (max_items >= (int64_t)1 << 31) return NQMC_ERR_UNSUPPORTED;   // ItemIter counts items in 32 bits
   int n_chunks = ctx->sm_count / s.n_mlp;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > max_items) n_chunks = (int)max_items;
