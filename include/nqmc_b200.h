@@ -276,6 +276,10 @@ int nqmc_debug_check_guards(nqmc_ctx* ctx);
 /* Guard mode only: device pointer of the named internal scratch buffer ("phi", "inv", "logabs", ...), else NULL.
  * For tests of the checker itself. */
 void* nqmc_debug_scratch_ptr(nqmc_ctx* ctx, const char* name);
+/* Host-side run of the work-item iterator of the persistent orbital kernels (csrc/nqmc_internal.cuh, ItemIter): writes
+ * the (walker block, electron-of-spin) pairs of items first, first + stride, ... (n of them); no GPU needed.  Tests
+ * compare it with item / ns, item % ns. */
+int nqmc_debug_item_iter(int32_t first, int32_t stride, int32_t ns, int64_t n, int32_t* walker_block, int32_t* electron);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */

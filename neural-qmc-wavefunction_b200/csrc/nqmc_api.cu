@@ -863,6 +863,13 @@ void* nqmc_debug_scratch_ptr(nqmc_ctx* ctx, const char* name) {
   return nullptr;
 }
 
+int nqmc_debug_item_iter(int32_t first, int32_t stride, int32_t ns, int64_t n, int32_t* wb, int32_t* e) {
+  if (first < 0 || stride < 1 || ns < 1 || n < 0 || !wb || !e) return NQMC_ERR_ARG;
+  ItemIter it(first, stride, ns);
+  for (int64_t i = 0; i < n; ++i, it.next()) { wb[i] = it.wb; e[i] = it.e; }
+  return NQMC_OK;
+}
+
 int64_t nqmc_launch_count(const nqmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 int nqmc_use_tensor_cores(nqmc_ctx* ctx, int enable) {

@@ -34,6 +34,7 @@ EXPORTS = [
     "nqmc_device_count", "nqmc_dev_alloc", "nqmc_dev_free", "nqmc_host_alloc", "nqmc_host_free", "nqmc_dev_memcpy",
     "nqmc_dev_copy_rows", "nqmc_dev_memset", "nqmc_stream_create", "nqmc_stream_destroy", "nqmc_stream_sync", "nqmc_stream_wait",
     "nqmc_mem_last_error", "nqmc_xla_ffi_available", "nqmc_gram", "nqmc_sr_workspace_bytes", "nqmc_sr_update", "nqmc_log_psi_grads", "nqmc_apply_update", "nqmc_debug_check_guards", "nqmc_debug_scratch_ptr",
+    "nqmc_debug_item_iter",
 ]
 
 
@@ -118,6 +119,7 @@ def load_library():
     lib.nqmc_debug_check_guards.argtypes = [vp]
     lib.nqmc_debug_scratch_ptr.argtypes = [vp, C.c_char_p]
     lib.nqmc_debug_scratch_ptr.restype = vp
+    lib.nqmc_debug_item_iter.argtypes = [C.c_int32, C.c_int32, C.c_int32, i64, vp, vp]
     lib.nqmc_device_count.argtypes = []
     lib.nqmc_dev_alloc.argtypes = [C.c_int, sz, C.POINTER(vp)]
     lib.nqmc_dev_free.argtypes = [C.c_int, vp]

@@ -167,3 +167,23 @@ def test_checkpoint_roundtrip_host(tmp_path):
     assert np.array_equal(P.ravel(st2.params), P.ravel(params))
     assert np.array_equal(st2.opt_state["mu"], opt["mu"]) and np.array_equal(st2.opt_state["nu"], opt["nu"])
     assert np.array_equal(st2.sampler_state.positions, ss.positions) and st2.sampler_state.n_steps == 11
+
+
+def test_item_iterator_matches_div_mod():
+    """The persistent orbital kernels advance (walker block, electron) incrementally instead of dividing per tile
+    (csrc/nqmc_internal.cuh, ItemIter); the same struct, run on the host through the C ABI, against item // ns, item % ns."""
+    import ctypes
+    lib = _native.load_library()
+    rng = np.random.default_rng(0)
+    cases = [(0, 1, 1), (0, 37, 2), (36, 37, 2), (5, 148, 5), (147, 148, 3), (3, 7, 10), (0, 29, 4), (11, 14, 5)]
+    cases += [(int(rng.integers(0, 200)), int(rng.integers(1, 200)), int(rng.integers(1, 11))) for _ in range(40)]
+    n = 5000
+    for first, stride, ns in cases:
+        wb = np.empty(n, np.int32); e = np.empty(n, np.int32)
+        rc = lib.nqmc_debug_item_iter(first, stride, ns, n, ctypes.c_void_p(wb.ctypes.data), ctypes.c_void_p(e.ctypes.data))
+        assert rc == 0
+        items = first + stride * np.arange(n, dtype=np.int64)
+        assert np.array_equal(wb, items // ns), (first, stride, ns)
+        assert np.array_equal(e, items % ns), (first, stride, ns)
+    bad = np.empty(1, np.int32)
+    assert lib.nqmc_debug_item_iter(0, 0, 2, 1, ctypes.c_void_p(bad.ctypes.data), ctypes.c_void_p(bad.ctypes.data)) != 0
