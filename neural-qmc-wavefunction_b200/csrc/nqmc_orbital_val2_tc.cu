@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TCT, 1)
   nq_pdl_wait();                              // everything above read theta only; the positions come from the predecessor
   const int64_t nwb = (W + ROWS - 1) / ROWS;
   const int64_t n_items = nwb * ns;
-  const int64_t n_tiles = chunk < n_items ? (n_items - chunk + n_chunks - 1) / n_chunks : 0;   // tiles of this CTA
+  const int n_tiles = chunk < n_items ? (int)((n_items - chunk + n_chunks - 1) / n_chunks) : 0;   // tiles of this CTA (the launcher keeps n_items below 2^31)
   // step s = -2 .. n_tiles-1:  W_a(tile s+2), W_b(tile s+1), W_c(tile s) ; barrier ; issue L1(s+2), U2(s+1)
 
   if (!worker) {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(TCT, 1)
     const uint32_t leader = elect_one();
     const uint64_t b1h = umma_desc(smem_u32(W1hi), H * 16, 128), b1l = umma_desc(smem_u32(W1lo), H * 16, 128);
     const uint64_t b2h = umma_desc(smem_u32(W2hi), H * 16, 128), b2l = umma_desc(smem_u32(W2lo), H * 16, 128);
-    for (int64_t st = -2; st < n_tiles; ++st) {
+    for (int st = -2; st < n_tiles; ++st) {
       tile_barrier();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (iw == 0 && st + 2 < n_tiles) {                         // D1 = [features | 1] x [W1 ; b1]
@@ -236,15 +236,15 @@ __global__ void __launch_bounds__(TCT, 1)
   auto fetch = [&]() {                                          // tiles are requested in order: 0, 1, 2, ...
     int64_t w = (int64_t)it_f.wb * ROWS + row;
     if (w >= W) w = W - 1;
-    const int e = elec0 + it_f.e;
-    nx = r[(int64_t)(3 * e + 0) * W + w];
-    ny = r[(int64_t)(3 * e + 1) * W + w];
-    nz = r[(int64_t)(3 * e + 2) * W + w];
+    const float* p = r + (int64_t)(3 * (elec0 + it_f.e)) * W + w;   // one address, then two strides of W
+    nx = p[0];
+    ny = p[W];
+    nz = p[2 * W];
     it_f.next();
   };
   if (n_tiles > 0) fetch();
 #pragma unroll 2
-  for (int64_t st = -2; st < n_tiles; ++st) {
+  for (int st = -2; st < n_tiles; ++st) {
     // ---- W_a: features of tile st+2 -> FA[(st+2)&1].  Quarter q takes nuclei q, q+4, ..; quarter 0 also x, y, z, 1.
     // The three work items of a step touch different tiles and are independent.  The four warps that share an SM
     // sub-partition (the four quarters of 32 rows) leave the step barrier together; if all of them run a, b, c they
