@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(TCT, 1)
     auto fetch = [&]() {                                       // tiles are requested in order: chunk, chunk + n_chunks, ...
       int64_t w = (int64_t)nxt.wb * ROWS + row;
       if (w >= W) w = W - 1;
-      const int e = elec0 + nxt.e;
-      nx = r[(int64_t)(3 * e + 0) * W + w];
-      ny = r[(int64_t)(3 * e + 1) * W + w];
-      nz = r[(int64_t)(3 * e + 2) * W + w];
+      const float* p = r + (int64_t)(3 * (elec0 + nxt.e)) * W + w;   // one address, then two strides of W
+      nx = p[0];
+      ny = p[W];
+      nz = p[2 * W];
       nxt.next();
     };
     // per nucleus: d, exp(-d), unit vector, 2/d -- in registers for all 8 chunks.  With s = wd - e we the five
